@@ -1,0 +1,149 @@
+/*
+ * libtorj_cuda.so — C ABI of the B200-native TorJ ray-tracing hot path.
+ *
+ * The reference (ProjectTorreyPines/TorJ.jl) has no FFI: its seam is the Julia function level.  Each entry
+ * point below names the reference interface it replaces (file:line into the reference repository); the Julia
+ * `ccall` shim a maintainer would add is shown in INTEGRATION.md and mirrored, name for name, by the Python
+ * host package torj_jl_b200 (Julia is not installed in this environment).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on a library / CUDA failure; torj_last_error() has the text.
+ *   - per-ray physics failures never abort a batch: they are reported in status[] (TORJ_RAY_*).
+ *   - the caller owns every host buffer; nothing is retained past the call that received it.
+ *   - 2-D tables are "R fastest" (a Julia Matrix[nR+2, nZ+2] passed as is); ray positions/directions are
+ *     component-major [3][n] (a Julia Matrix[n,3] passed as is, reference src/launch.jl:84-85).
+ *   - all arithmetic is FP64.  There is no CPU fallback: without a CUDA device torj_ctx_create fails.
+ */
+#ifndef TORJ_CUDA_H
+#define TORJ_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TORJ_ABI_VERSION 1
+
+typedef struct torj_ctx torj_ctx;       /* one per (process, device): stream, quadrature nodes, launch counter */
+typedef struct torj_plasma torj_plasma; /* device-resident equilibrium tables (reference struct Plasma, src/plasma.jl:2-14) */
+typedef struct torj_bundle torj_bundle; /* device-resident ray bundle, its state and results */
+
+/* per-ray status */
+enum {
+    TORJ_RAY_OK = 0,
+    TORJ_RAY_CUTOFF_AT_ENTRY = 1, /* reference src/solve.jl:55-59 returns (false, nothing) */
+    TORJ_RAY_INIT_FAILED = 2,     /* bisection bracket (src/solve.jl:29), asserts src/solve.jl:32,138,141, Newton failure */
+    TORJ_RAY_LEFT_GRID = 3,
+    TORJ_RAY_MAX_STEPS = 4,
+    TORJ_RAY_NAN = 5,
+    TORJ_RAY_TRAJ_TRUNCATED = 6   /* trajectory window full; tracing and deposition still completed */
+};
+
+/* Solver constants hard-coded in the reference, carried here with the reference values as defaults. */
+typedef struct torj_options {
+    int32_t scheme;                /* 0 = Tsit5: what `solve(prob)` runs, the `OwrenZen3()` at src/solve.jl:156 being
+                                      passed as the parameter object; 1 = OwrenZen3 (the scheme the source names) */
+    int32_t n_segments;            /* 100   src/solve.jl:145 */
+    double dtmax;                  /* 1e-4  src/solve.jl:157 */
+    double abstol;                 /* 1e-6  src/solve.jl:157 */
+    double reltol;                 /* 1e-6  src/solve.jl:157 */
+    double psi_stop;               /* 1.0   src/solve.jl:174 */
+    double p_stop;                 /* 1e-6  src/solve.jl:176 */
+    double te_min;                 /* 20 eV src/absorption.jl:194 */
+    int32_t max_harmonic;          /* 3     src/absorption.jl:199 */
+    int32_t max_steps_per_segment; /* safety cap, 100000 */
+} torj_options;
+
+typedef struct torj_counters {
+    int64_t n_acc;   /* accepted integrator steps (the "ray-steps" of the headline metric) */
+    int64_t n_rej;   /* rejected steps */
+    int64_t n_rhs;   /* evaluations of gradΛ! (src/solve.jl:85-95) */
+    int64_t n_alpha; /* abs_Albajar_fast calls past the Te gate (src/absorption.jl:194) */
+    int64_t n_harm;  /* harmonic integrals evaluated (src/absorption.jl:217) */
+    int64_t n_rays_ok;
+} torj_counters;
+
+typedef struct torj_grid {
+    int32_t nR, nZ;        /* data points per axis; coefficient tables are (nR+2) x (nZ+2) */
+    double R_first, R_last;
+    double Z_first, Z_last;
+} torj_grid;
+
+void torj_options_default(torj_options* o);
+const char* torj_last_error(void);
+int torj_abi_version(void);
+
+/* --- context ---------------------------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to launch on (e.g. the caller's current stream) or NULL for a private stream. */
+int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out);
+void torj_ctx_destroy(torj_ctx* ctx);
+int torj_ctx_sync(torj_ctx* ctx);
+/* kernels launched by this library on ctx since creation */
+int64_t torj_ctx_launch_count(const torj_ctx* ctx);
+
+/* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64). */
+int torj_abs_init(torj_ctx* ctx, int32_t n, const double* nodes, const double* weights);
+
+/* --- equilibrium ------------------------------------------------------------------------------------------- */
+/* Host helper: cubic B-spline prefilter of cubic_spline_interpolation((r,z), data) — reference src/plasma.jl:36-41
+ * (Interpolations.jl BSpline(Cubic(Line(OnGrid())))).  data: nR x nZ, R fastest; coef out: (nR+2) x (nZ+2). */
+int torj_bspline_prefilter_2d(int32_t nR, int32_t nZ, const double* data, double* coef);
+int torj_bspline_prefilter_1d(int32_t n, const double* data, double* coef);
+
+/* Uploads what the Julia shim extracts from a `Plasma` (src/plasma.jl:2-14): six coefficient tables, the 1-D
+ * V(psi_N) spline (n_vol data points -> n_vol+2 coefficients on the uniform range vol_psi0 + k*vol_dpsi) and
+ * psi_prof_max. */
+int torj_plasma_create(torj_ctx* ctx, const torj_grid* grid, const double* coef_psi, const double* coef_lnne,
+                       const double* coef_lnTe, const double* coef_BR, const double* coef_BZ, const double* coef_Bphi,
+                       const double* vol_coef, int32_t n_vol, double vol_psi0, double vol_dpsi, double psi_prof_max,
+                       torj_plasma** out);
+void torj_plasma_destroy(torj_plasma* p);
+
+/* Field probes at Cartesian points x[3][n] (tests of reference src/plasma.jl:61-89 / src/dispersion.jl:7-15,
+ * cf. reference test/tests/test_trajectory.jl). out[11][n]: psi, ne, Te, Bx, By, Bz, X, Y, N_par, Lambda, alpha */
+int torj_probe(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64_t n, const double* x, const double* N,
+               double freq_hz, int32_t mode, double* out);
+/* du = gradΛ!(u) for u[7][n] (reference src/solve.jl:85-95) */
+int torj_rhs(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64_t n, const double* u, double freq_hz,
+             int32_t mode, double* du);
+
+/* --- resident bundle API (bench "value": inputs already in HBM) --------------------------------------------- */
+/* freq_hz/mode: per ray when per_ray_fm != 0, else length 1. */
+int torj_bundle_create(torj_ctx* ctx, int64_t n_rays, const double* pos, const double* dir, const double* weight,
+                       const double* freq_hz, const int32_t* mode, int32_t per_ray_fm, torj_bundle** out);
+void torj_bundle_destroy(torj_bundle* b);
+/* Trajectories are kept for rays [traj_first, traj_first+traj_count), up to traj_max_pts points each. */
+int torj_bundle_set_window(torj_bundle* b, int64_t traj_first, int64_t traj_count, int32_t traj_max_pts);
+/* Enqueues ray init + trace + profile finalize on the context stream; returns without synchronising.
+ * Replaces the parallel region and reduction of make_beam (reference src/solve.jl:219-240) and, per ray,
+ * make_ray (src/solve.jl:135-181) incl. power_deposition_profile (src/plasma.jl:91-151). */
+int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* opt, double s_max, int32_t n_psi,
+                      const double* psi_edges);
+/* Device pointer to n_psi+2 doubles: dP_dV[n_psi], deposited_power, sum of weights — for a caller-side
+ * NCCL all-reduce (sum) across GPUs; valid after torj_bundle_trace, ordered on the context stream. */
+void* torj_bundle_device_profile(torj_bundle* b);
+/* Synchronises and copies results to the host (any pointer may be NULL). */
+int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, double* P_final,
+                        double* P_deposited_ray, int32_t* n_points, int32_t* status, torj_counters* counters);
+/* Trajectory window to the host: arrays [traj_count][traj_max_pts] (s, P, dP_ds), [traj_count][3][traj_max_pts]
+ * (xyz) and the per-ray profile [traj_count][n_psi]; any pointer may be NULL. */
+int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, double* dP_ds, double* dP_dV_ray);
+
+/* --- one-shot host-buffer call: what the Julia make_ray / make_beam shims ccall ------------------------------ */
+int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
+               const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
+               double s_max, int32_t n_psi, const double* psi_edges,
+               /* out */ double* dP_dV, double* deposited_power, double* P_final, double* P_deposited_ray,
+               int32_t* n_points, int32_t* status,
+               /* optional trajectories */ int64_t traj_first, int64_t traj_count, int32_t traj_max_pts, double* traj_s,
+               double* traj_xyz, double* traj_P, double* traj_dP_ds, double* traj_dP_dV_ray, torj_counters* counters);
+
+/* --- measurement ------------------------------------------------------------------------------------------- */
+/* Register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). */
+int torj_fp64_peak(torj_ctx* ctx, int32_t iters, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORJ_CUDA_H */

@@ -1,0 +1,567 @@
+// Host side of libtorj_cuda.so: the C ABI declared in include/torj_cuda.h.
+// Plain CUDA runtime; no torch types, no CPU fallback (every entry point needs a CUDA device).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/torj_cuda.h"
+#include "torj_kernels.cuh"
+
+using namespace torj;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            char buf_[512];                                                                               \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            g_err = buf_;                                                                                 \
+            return 1;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+
+#define FAIL(msg) do { g_err = (msg); return 2; } while (0)
+
+struct torj_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool gl_set = false;
+    int num_sms = 0;
+    int64_t launches = 0;
+};
+
+struct torj_plasma {
+    torj_ctx* ctx = nullptr;
+    DevTables T{};
+    double2* dA = nullptr;
+    double2* dB = nullptr;
+    DevTables* dT = nullptr;  // T mirrored in global memory
+    // host copy of the V(psi_N) spline (reference src/plasma.jl:42-44)
+    std::vector<double> vol_c;
+    int n_vol = 0;
+    double vol_x0 = 0, vol_h = 1;
+};
+
+struct torj_bundle {
+    torj_ctx* ctx = nullptr;
+    int64_t n = 0;
+    BundleDev B{};
+    int per_ray_fm = 0;
+    // owned device buffers
+    double *d_pos = nullptr, *d_dir = nullptr, *d_w = nullptr, *d_freq = nullptr, *d_u0 = nullptr, *d_s0 = nullptr,
+           *d_psil = nullptr, *d_Pf = nullptr, *d_Pdep = nullptr;
+    int *d_mode = nullptr, *d_status = nullptr, *d_npts = nullptr;
+    // deposition
+    int n_psi = 0;
+    double *d_edges = nullptr, *d_bins = nullptr, *d_dV = nullptr, *d_profile = nullptr;
+    unsigned long long *d_queue = nullptr, *d_counters = nullptr;
+    // trajectory window
+    int64_t traj_first = 0, traj_count = 0;
+    int traj_max = 0;
+    double *d_ts = nullptr, *d_txyz = nullptr, *d_tP = nullptr, *d_tdP = nullptr, *d_tprof = nullptr;
+    int traj_prof_npsi = 0;
+};
+
+static int set_device(const torj_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+extern "C" {
+
+const char* torj_last_error(void) { return g_err.c_str(); }
+int torj_abi_version(void) { return TORJ_ABI_VERSION; }
+
+void torj_options_default(torj_options* o) {
+    o->scheme = 0;
+    o->n_segments = 100;
+    o->dtmax = 1e-4;
+    o->abstol = 1e-6;
+    o->reltol = 1e-6;
+    o->psi_stop = 1.0;
+    o->p_stop = 1e-6;
+    o->te_min = 20.0;
+    o->max_harmonic = 3;
+    o->max_steps_per_segment = 100000;
+}
+
+static void fill_tableaux(Tableau t[2]) {
+    memset(t, 0, 2 * sizeof(Tableau));
+    double(*a)[7] = t[0].a;  // Tsit5
+    a[1][0] = 0.161;
+    a[2][0] = -0.008480655492356989; a[2][1] = 0.335480655492357;
+    a[3][0] = 2.8971530571054935; a[3][1] = -6.359448489975075; a[3][2] = 4.3622954328695815;
+    a[4][0] = 5.325864828439257; a[4][1] = -11.748883564062828; a[4][2] = 7.4955393428898365; a[4][3] = -0.09249506636175525;
+    a[5][0] = 5.86145544294642; a[5][1] = -12.92096931784711; a[5][2] = 8.159367898576159; a[5][3] = -0.071584973281401;
+    a[5][4] = -0.028269050394068383;
+    a[6][0] = 0.09646076681806523; a[6][1] = 0.01; a[6][2] = 0.4798896504144996; a[6][3] = 1.379008574103742;
+    a[6][4] = -3.290069515436081; a[6][5] = 2.324710524099774;
+    const double bt[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                          0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+    for (int i = 0; i < 7; ++i) t[0].bt[i] = bt[i];
+    a = t[1].a;  // OwrenZen3
+    a[1][0] = 12.0 / 23.0;
+    a[2][0] = -68.0 / 375.0; a[2][1] = 368.0 / 375.0;
+    a[3][0] = 31.0 / 144.0; a[3][1] = 529.0 / 1152.0; a[3][2] = 125.0 / 384.0;
+    t[1].bt[0] = 25.0 / 144.0; t[1].bt[1] = -575.0 / 1152.0; t[1].bt[2] = 125.0 / 384.0;
+}
+
+int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
+    if (!out) FAIL("torj_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_err = std::string("torj_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); libtorj_cuda has no CPU path";
+        return 1;
+    }
+    if (device < 0 || device >= ndev) FAIL("torj_ctx_create: bad device index");
+    CK(cudaSetDevice(device));
+    torj_ctx* c = new torj_ctx();
+    c->device = device;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+    Tableau t[2];
+    fill_tableaux(t);
+    CK(cudaMemcpyToSymbol(c_tab, t, sizeof t));
+    // Bessel series coefficients c[n][k] = (-1)^k n!/(k!(n+k)!)
+    double bc[5][TORJ_BESS_K];
+    for (int n = 0; n < 5; ++n) {
+        bc[n][0] = 1.0;
+        for (int k = 1; k < TORJ_BESS_K; ++k) bc[n][k] = -bc[n][k - 1] / ((double)k * (double)(n + k));
+    }
+    CK(cudaMemcpyToSymbol(c_bess, bc, sizeof bc));
+    *out = c;
+    return 0;
+}
+
+void torj_ctx_destroy(torj_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int torj_ctx_sync(torj_ctx* c) {
+    if (set_device(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int64_t torj_ctx_launch_count(const torj_ctx* c) { return c->launches; }
+
+int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* weights) {
+    if (n < 1 || n > TORJ_MAX_GL) FAIL("torj_abs_init: need 1 <= n <= 64");
+    if (set_device(c)) return 1;
+    GLNodes g;
+    memset(&g, 0, sizeof g);
+    g.n = n;
+    for (int i = 0; i < n; ++i) {
+        g.t[i] = nodes[i];
+        g.w[i] = weights[i];
+        g.sq[i] = std::sqrt(1.0 - nodes[i] * nodes[i]);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyToSymbol(c_gl, &g, sizeof g));
+    c->gl_set = true;
+    return 0;
+}
+
+// ---- B-spline prefilter (host): rows (1/6, 2/3, 1/6), natural ends c0-2c1+c2 = 0 -> c[1]=y[0], c[n]=y[n-1]
+static void prefilter_line(const double* y, size_t ys, int n, double* c, size_t cs) {
+    std::vector<double> sol(n), cp(n), dp(n);
+    sol[0] = y[0];
+    sol[n - 1] = y[(size_t)(n - 1) * ys];
+    if (n > 2) {
+        const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+        int m = n - 2;
+        cp[0] = a / b;
+        dp[0] = (y[ys] - a * sol[0]) / b;
+        for (int k = 1; k < m; ++k) {
+            double r = y[(size_t)(k + 1) * ys];
+            if (k == m - 1) r -= a * sol[n - 1];
+            double den = b - a * cp[k - 1];
+            cp[k] = a / den;
+            dp[k] = (r - a * dp[k - 1]) / den;
+        }
+        if (m == 1) dp[0] = (y[ys] - a * sol[0] - a * sol[n - 1]) / b;
+        sol[m] = dp[m - 1];
+        for (int k = m - 2; k >= 0; --k) sol[k + 1] = dp[k] - cp[k] * sol[k + 2];
+    }
+    for (int k = 0; k < n; ++k) c[(size_t)(k + 1) * cs] = sol[k];
+    c[0] = 2.0 * sol[0] - sol[1];
+    c[(size_t)(n + 1) * cs] = 2.0 * sol[n - 1] - sol[n - 2];
+}
+
+int torj_bspline_prefilter_1d(int32_t n, const double* data, double* coef) {
+    if (n < 2) FAIL("torj_bspline_prefilter_1d: n < 2");
+    prefilter_line(data, 1, n, coef, 1);
+    return 0;
+}
+
+int torj_bspline_prefilter_2d(int32_t nR, int32_t nZ, const double* data, double* coef) {
+    if (nR < 2 || nZ < 2) FAIL("torj_bspline_prefilter_2d: need at least 2 points per axis");
+    size_t sr = (size_t)nR + 2;
+    std::vector<double> tmp(sr * nZ);
+    for (int j = 0; j < nZ; ++j) prefilter_line(data + (size_t)j * nR, 1, nR, tmp.data() + (size_t)j * sr, 1);
+    for (size_t i = 0; i < sr; ++i) prefilter_line(tmp.data() + i, sr, nZ, coef + i, sr);
+    return 0;
+}
+
+int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, const double* coef_lnne,
+                       const double* coef_lnTe, const double* coef_BR, const double* coef_BZ, const double* coef_Bphi,
+                       const double* vol_coef, int32_t n_vol, double vol_psi0, double vol_dpsi, double psi_prof_max,
+                       torj_plasma** out) {
+    if (!c || !g || !out) FAIL("torj_plasma_create: NULL argument");
+    if (g->nR < 2 || g->nZ < 2 || n_vol < 2) FAIL("torj_plasma_create: grid too small");
+    if (set_device(c)) return 1;
+    torj_plasma* p = new torj_plasma();
+    p->ctx = c;
+    size_t nodes = (size_t)(g->nR + 2) * (g->nZ + 2);
+    std::vector<double2> hA(2 * nodes), hB(nodes);
+    for (size_t k = 0; k < nodes; ++k) {
+        hA[2 * k] = make_double2(coef_BR[k], coef_BZ[k]);
+        hA[2 * k + 1] = make_double2(coef_Bphi[k], coef_lnne[k]);
+        hB[k] = make_double2(coef_lnTe[k], coef_psi[k]);
+    }
+    CK(cudaMalloc(&p->dA, 2 * nodes * sizeof(double2)));
+    CK(cudaMalloc(&p->dB, nodes * sizeof(double2)));
+    CK(cudaMemcpyAsync(p->dA, hA.data(), 2 * nodes * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(p->dB, hB.data(), nodes * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    DevTables& T = p->T;
+    T.A = p->dA; T.B = p->dB;
+    T.nR = g->nR; T.nZ = g->nZ; T.row = g->nR + 2;
+    T.r0 = g->R_first; T.z0 = g->Z_first;
+    double hr = (g->R_last - g->R_first) / (double)(g->nR - 1), hz = (g->Z_last - g->Z_first) / (double)(g->nZ - 1);
+    T.inv_hr = 1.0 / hr; T.inv_hz = 1.0 / hz;
+    T.rlast = g->R_first + hr * (g->nR - 1); T.zlast = g->Z_first + hz * (g->nZ - 1);
+    T.psi_prof_max = psi_prof_max;
+    CK(cudaMalloc(&p->dT, sizeof(DevTables)));
+    CK(cudaMemcpy(p->dT, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
+    p->vol_c.assign(vol_coef, vol_coef + n_vol + 2);
+    p->n_vol = n_vol; p->vol_x0 = vol_psi0; p->vol_h = vol_dpsi;
+    *out = p;
+    return 0;
+}
+
+void torj_plasma_destroy(torj_plasma* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->dA);
+    cudaFree(p->dB);
+    cudaFree(p->dT);
+    delete p;
+}
+
+// V(psi_N): 1-D cubic B-spline with Line extrapolation (reference src/plasma.jl:44,109,113)
+static double volume_at(const torj_plasma* p, double x) {
+    const int n = p->n_vol;
+    double xl = p->vol_x0 + p->vol_h * (n - 1);
+    double xc = std::min(std::max(x, p->vol_x0), xl);
+    double u = (xc - p->vol_x0) / p->vol_h + 1.0;
+    int i = (int)std::floor(u);
+    i = std::min(std::max(i, 1), n - 1);
+    double d = u - i, e = 1.0 - d;
+    double w[4] = {e * e * e / 6.0, 2.0 / 3.0 - d * d + d * d * d / 2.0, 2.0 / 3.0 - e * e + e * e * e / 2.0, d * d * d / 6.0};
+    double dw[4] = {-e * e / 2.0 / p->vol_h, (-2.0 * d + 1.5 * d * d) / p->vol_h, (2.0 * e - 1.5 * e * e) / p->vol_h,
+                    d * d / 2.0 / p->vol_h};
+    double v = 0, dv = 0;
+    for (int k = 0; k < 4; ++k) { v += w[k] * p->vol_c[i - 1 + k]; dv += dw[k] * p->vol_c[i - 1 + k]; }
+    if (xc != x) v += (x - xc) * dv;
+    return v;
+}
+
+static SolverOpts to_sopts(const torj_options* o, double s_max) {
+    torj_options d;
+    torj_options_default(&d);
+    if (o) d = *o;
+    SolverOpts s;
+    s.n_segments = d.n_segments; s.max_steps = d.max_steps_per_segment; s.s_max = s_max; s.dtmax = d.dtmax;
+    s.abstol = d.abstol; s.reltol = d.reltol; s.psi_stop = d.psi_stop; s.p_stop = d.p_stop; s.te_min = d.te_min;
+    s.max_harmonic = d.max_harmonic;
+    return s;
+}
+
+int torj_probe(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t n, const double* x, const double* N,
+               double freq_hz, int32_t mode, double* out) {
+    if (!c->gl_set) FAIL("The weights and abscissae for the absorption were never initialized. Call `abs_Al_init` before using the absorption.");
+    if (set_device(c)) return 1;
+    SolverOpts so = to_sopts(opt, 1.0);
+    double *dx, *dN, *dout;
+    CK(cudaMalloc(&dx, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&dN, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&dout, 11 * n * sizeof(double)));
+    CK(cudaMemcpyAsync(dx, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dN, N, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, dout);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, 11 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dx); cudaFree(dN); cudaFree(dout);
+    return 0;
+}
+
+int torj_rhs(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t n, const double* u, double freq_hz,
+             int32_t mode, double* du) {
+    if (!c->gl_set) FAIL("The weights and abscissae for the absorption were never initialized. Call `abs_Al_init` before using the absorption.");
+    if (set_device(c)) return 1;
+    SolverOpts so = to_sopts(opt, 1.0);
+    double *d_u, *d_du;
+    CK(cudaMalloc(&d_u, 7 * n * sizeof(double)));
+    CK(cudaMalloc(&d_du, 7 * n * sizeof(double)));
+    CK(cudaMemcpyAsync(d_u, u, 7 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, d_du);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(du, d_du, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_u); cudaFree(d_du);
+    return 0;
+}
+
+// ---- bundle ---------------------------------------------------------------------------------------------------
+static void free_traj(torj_bundle* b) {
+    cudaFree(b->d_ts); cudaFree(b->d_txyz); cudaFree(b->d_tP); cudaFree(b->d_tdP); cudaFree(b->d_tprof);
+    b->d_ts = b->d_txyz = b->d_tP = b->d_tdP = b->d_tprof = nullptr;
+    b->traj_prof_npsi = 0;
+}
+
+int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* dir, const double* weight,
+                       const double* freq_hz, const int32_t* mode, int32_t per_ray_fm, torj_bundle** out) {
+    if (!c || !out || n < 1) FAIL("torj_bundle_create: bad argument");
+    if (set_device(c)) return 1;
+    torj_bundle* b = new torj_bundle();
+    b->ctx = c; b->n = n; b->per_ray_fm = per_ray_fm;
+    size_t nf = per_ray_fm ? (size_t)n : 1;
+    CK(cudaMalloc(&b->d_pos, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_dir, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_w, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_freq, nf * sizeof(double)));
+    CK(cudaMalloc(&b->d_mode, nf * sizeof(int)));
+    CK(cudaMalloc(&b->d_u0, 7 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_s0, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_psil, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_Pf, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_Pdep, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_status, n * sizeof(int)));
+    CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
+    CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_counters, 6 * sizeof(unsigned long long)));
+    CK(cudaMemcpyAsync(b->d_pos, pos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_dir, dir, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_w, weight, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_freq, freq_hz, nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_mode, mode, nf * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // host buffers may be released by the caller on return
+    BundleDev& B = b->B;
+    B.n_rays = n; B.pos = b->d_pos; B.dir = b->d_dir; B.weight = b->d_w; B.freq = b->d_freq; B.mode = b->d_mode;
+    B.per_ray_fm = per_ray_fm; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
+    B.P_final = b->d_Pf; B.P_dep = b->d_Pdep; B.n_points = b->d_npts;
+    *out = b;
+    return 0;
+}
+
+void torj_bundle_destroy(torj_bundle* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_pos); cudaFree(b->d_dir); cudaFree(b->d_w); cudaFree(b->d_freq); cudaFree(b->d_mode); cudaFree(b->d_u0);
+    cudaFree(b->d_s0); cudaFree(b->d_psil); cudaFree(b->d_Pf); cudaFree(b->d_Pdep); cudaFree(b->d_status); cudaFree(b->d_npts);
+    cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
+    cudaFree(b->d_profile);
+    free_traj(b);
+    delete b;
+}
+
+int torj_bundle_set_window(torj_bundle* b, int64_t first, int64_t count, int32_t max_pts) {
+    if (set_device(b->ctx)) return 1;
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    free_traj(b);
+    if (count <= 0 || max_pts <= 0) { b->traj_first = 0; b->traj_count = 0; b->traj_max = 0; return 0; }
+    if (first < 0 || first + count > b->n) FAIL("torj_bundle_set_window: window outside the bundle");
+    b->traj_first = first; b->traj_count = count; b->traj_max = max_pts;
+    size_t m = (size_t)count * max_pts;
+    CK(cudaMalloc(&b->d_ts, m * sizeof(double)));
+    CK(cudaMalloc(&b->d_txyz, 3 * m * sizeof(double)));
+    CK(cudaMalloc(&b->d_tP, m * sizeof(double)));
+    CK(cudaMalloc(&b->d_tdP, m * sizeof(double)));
+    return 0;
+}
+
+int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* opt, double s_max, int32_t n_psi,
+                      const double* psi_edges) {
+    torj_ctx* c = b->ctx;
+    if (!c->gl_set) FAIL("The weights and abscissae for the absorption were never initialized. Call `abs_Al_init` before using the absorption.");
+    if (n_psi < 2) FAIL("torj_bundle_trace: need at least 2 psi levels");
+    for (int j = 1; j < n_psi; ++j) if (!(psi_edges[j] > psi_edges[j - 1])) FAIL("torj_bundle_trace: psi_dP_dV must be strictly increasing");
+    torj_options od;
+    torj_options_default(&od);
+    if (opt) od = *opt;
+    if (od.scheme != 0 && od.scheme != 1) FAIL("torj_bundle_trace: scheme must be 0 (Tsit5) or 1 (OwrenZen3)");
+    if (od.n_segments < 1) FAIL("torj_bundle_trace: n_segments < 1");
+    if (set_device(c)) return 1;
+    cudaStream_t st = c->stream;
+    if (b->n_psi != n_psi) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV); cudaFree(b->d_profile);
+        CK(cudaMalloc(&b->d_edges, n_psi * sizeof(double)));
+        CK(cudaMalloc(&b->d_bins, (n_psi + 2) * sizeof(double)));
+        CK(cudaMalloc(&b->d_dV, n_psi * sizeof(double)));
+        CK(cudaMalloc(&b->d_profile, (n_psi + 2) * sizeof(double)));
+        b->n_psi = n_psi;
+    }
+    if (b->traj_count > 0 && b->traj_prof_npsi != n_psi) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(b->d_tprof);
+        CK(cudaMalloc(&b->d_tprof, (size_t)b->traj_count * n_psi * sizeof(double)));
+        b->traj_prof_npsi = n_psi;
+    }
+    std::vector<double> dV(n_psi, 1.0);
+    for (int j = 0; j + 1 < n_psi; ++j) dV[j] = volume_at(p, psi_edges[j + 1]) - volume_at(p, psi_edges[j]);
+    CK(cudaMemcpyAsync(b->d_edges, psi_edges, n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_dV, dV.data(), n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // dV is a local; psi_edges belongs to the caller
+    CK(cudaMemsetAsync(b->d_bins, 0, (n_psi + 2) * sizeof(double), st));
+    CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 6 * sizeof(unsigned long long), st));
+    if (b->traj_count > 0) CK(cudaMemsetAsync(b->d_tprof, 0, (size_t)b->traj_count * n_psi * sizeof(double), st));
+
+    SolverOpts so = to_sopts(&od, s_max);
+    k_ray_init<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so);
+    c->launches++;
+    CK(cudaGetLastError());
+
+    TraceArgs a;
+    a.T = p->T; a.Tg = p->dT; a.B = b->B; a.O = so;
+    a.J.first = b->traj_first; a.J.count = b->traj_count; a.J.max_pts = b->traj_max;
+    a.J.s = b->d_ts; a.J.xyz = b->d_txyz; a.J.P = b->d_tP; a.J.dP = b->d_tdP; a.J.prof = b->d_tprof;
+    a.n_psi = n_psi; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
+    size_t smem = 2 * (size_t)n_psi * sizeof(double);
+    int bps = 0;
+    int64_t warps = (b->n + 31) / 32;
+    int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);
+    if (od.scheme == 0) {
+        CK(cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<0>, TORJ_TPB, smem));
+    } else {
+        CK(cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<1>, TORJ_TPB, smem));
+    }
+    if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
+    int64_t grid = std::min<int64_t>((int64_t)c->num_sms * bps, blocks_needed);  // persistent: resident CTAs only
+    if (od.scheme == 0) k_trace<0><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+    else k_trace<1><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    k_finalize<<<(n_psi + 2 + 127) / 128, 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->d_profile);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+void* torj_bundle_device_profile(torj_bundle* b) { return b->d_profile; }
+
+int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, double* P_final, double* P_dep,
+                        int32_t* n_points, int32_t* status, torj_counters* counters) {
+    torj_ctx* c = b->ctx;
+    if (set_device(c)) return 1;
+    cudaStream_t st = c->stream;
+    if (b->n_psi == 0) FAIL("torj_bundle_results: nothing traced yet");
+    std::vector<double> prof(b->n_psi + 2);
+    CK(cudaMemcpyAsync(prof.data(), b->d_profile, (b->n_psi + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (P_final) CK(cudaMemcpyAsync(P_final, b->d_Pf, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (P_dep) CK(cudaMemcpyAsync(P_dep, b->d_Pdep, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (n_points) CK(cudaMemcpyAsync(n_points, b->d_npts, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, b->d_status, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned long long cn[6];
+    CK(cudaMemcpyAsync(cn, b->d_counters, sizeof cn, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (dP_dV) memcpy(dP_dV, prof.data(), b->n_psi * sizeof(double));
+    if (deposited_power) *deposited_power = prof[b->n_psi];
+    if (counters) {
+        counters->n_acc = (int64_t)cn[0]; counters->n_rej = (int64_t)cn[1]; counters->n_rhs = (int64_t)cn[2];
+        counters->n_alpha = (int64_t)cn[3]; counters->n_harm = (int64_t)cn[4]; counters->n_rays_ok = (int64_t)cn[5];
+    }
+    return 0;
+}
+
+int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, double* dP_ds, double* dP_dV_ray) {
+    torj_ctx* c = b->ctx;
+    if (b->traj_count <= 0) FAIL("torj_bundle_trajectories: no trajectory window set");
+    if (set_device(c)) return 1;
+    cudaStream_t st = c->stream;
+    size_t m = (size_t)b->traj_count * b->traj_max;
+    if (s) CK(cudaMemcpyAsync(s, b->d_ts, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (xyz) CK(cudaMemcpyAsync(xyz, b->d_txyz, 3 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (P) CK(cudaMemcpyAsync(P, b->d_tP, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dP_ds) CK(cudaMemcpyAsync(dP_ds, b->d_tdP, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dP_dV_ray && b->d_tprof)
+        CK(cudaMemcpyAsync(dP_dV_ray, b->d_tprof, (size_t)b->traj_count * b->n_psi * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (dP_dV_ray) {  // shell power -> dP/dV per ray (reference src/plasma.jl:141)
+        std::vector<double> dV(b->n_psi);
+        CK(cudaMemcpy(dV.data(), b->d_dV, b->n_psi * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t r = 0; r < b->traj_count; ++r) {
+            double* row = dP_dV_ray + (size_t)r * b->n_psi;
+            for (int j = 0; j + 1 < b->n_psi; ++j) row[j] /= dV[j];
+            row[b->n_psi - 1] = 0.0;
+        }
+    }
+    return 0;
+}
+
+int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
+               const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
+               double s_max, int32_t n_psi, const double* psi_edges, double* dP_dV, double* deposited_power,
+               double* P_final, double* P_dep, int32_t* n_points, int32_t* status, int64_t traj_first, int64_t traj_count,
+               int32_t traj_max_pts, double* traj_s, double* traj_xyz, double* traj_P, double* traj_dP_ds,
+               double* traj_dP_dV_ray, torj_counters* counters) {
+    torj_bundle* b = nullptr;
+    int rc = torj_bundle_create(c, n_rays, pos, dir, weight, freq_hz, mode, per_ray_fm, &b);
+    if (rc) return rc;
+    if (traj_count > 0) rc = torj_bundle_set_window(b, traj_first, traj_count, traj_max_pts);
+    if (!rc) rc = torj_bundle_trace(b, p, opt, s_max, n_psi, psi_edges);
+    if (!rc) rc = torj_bundle_results(b, dP_dV, deposited_power, P_final, P_dep, n_points, status, counters);
+    if (!rc && traj_count > 0) rc = torj_bundle_trajectories(b, traj_s, traj_xyz, traj_P, traj_dP_ds, traj_dP_dV_ray);
+    torj_bundle_destroy(b);
+    return rc;
+}
+
+int torj_fp64_peak(torj_ctx* c, int32_t iters, double* tflops, double* ms) {
+    if (set_device(c)) return 1;
+    double* d;
+    CK(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int blocks = c->num_sms * 8, threads = 256;
+    k_dfma<<<blocks, threads, 0, c->stream>>>(iters / 8 + 1, d);  // warm-up
+    c->launches++;
+    CK(cudaEventRecord(e0, c->stream));
+    k_dfma<<<blocks, threads, 0, c->stream>>>(iters, d);
+    c->launches++;
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    if (ms) *ms = t;
+    if (tflops) *tflops = flops / (t * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

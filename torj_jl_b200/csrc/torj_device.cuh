@@ -1,0 +1,556 @@
+// Device-side physics of the TorJ ray-tracing hot path for sm_100a (FP64 throughout).
+//
+//   spline tables / evaluation   <- reference src/plasma.jl:61-89 (Interpolations.jl cubic B-splines, Line extrapolation)
+//   cold dispersion + analytic   <- reference src/dispersion.jl:7-39 and the ForwardDiff gradients of
+//   Hamiltonian RHS                 src/solve.jl:85-95 (derived by hand here; the CPU oracle keeps dual numbers)
+//   Albajar absorption           <- reference src/absorption.jl:10-64,132-235
+//   streaming psi-shell deposit  <- reference src/plasma.jl:91-151 (see DESIGN.md for the algorithm and its bound)
+//
+// Table layout in HBM (one node = one (R,Z) B-spline coefficient position, R fastest):
+//   tabA[node] = { (B_R, B_Z), (B_phi, ln n_e) }   2 x double2   fields whose gradients the RHS needs
+//   tabB[node] = { ln T_e, psi_N }                 1 x double2   value-only field + the deposition field
+// so a 4x4 stencil is 4 contiguous runs of 128 B (A) and 64 B (B), read with 16-byte __ldg loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace torj {
+
+// reference src/constants.jl:13-26
+#define TORJ_C 2.99792458e8
+#define TORJ_EPS0 8.8541878128e-12
+#define TORJ_E 1.602176634e-19
+#define TORJ_ME 9.1093837015e-31
+
+#define TORJ_MAX_GL 64
+#define TORJ_BESS_K 24
+
+struct DevTables {
+    const double2* __restrict__ A;  // 2 double2 per node
+    const double2* __restrict__ B;  // 1 double2 per node
+    int nR, nZ, row;                // row = nR + 2 nodes per Z line
+    double r0, z0, inv_hr, inv_hz, rlast, zlast;
+    double psi_prof_max;
+};
+
+struct GLNodes {
+    double t[TORJ_MAX_GL];
+    double w[TORJ_MAX_GL];
+    double sq[TORJ_MAX_GL];  // sqrt(1 - t^2)
+    int n;
+};
+
+__constant__ GLNodes c_gl;
+// Horner coefficients of J_n(z) = (z/2)^n/n! * sum_k c[n][k] y^k, y = z^2/4 : c[n][k] = (-1)^k n! / (k! (n+k)!)
+__constant__ double c_bess[5][TORJ_BESS_K];
+
+struct RayConst {
+    double omega;    // 2 pi f
+    double cX;       // e^2/(eps0 m_e omega^2)
+    double cY;       // e/(m_e omega)
+    double w_over_c; // omega / c
+    double moded;    // +1 X-mode, -1 O-mode
+    double te_min;
+    int mode;
+    int max_harmonic;
+};
+
+__device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te_min, int max_harmonic) {
+    RayConst rc;
+    rc.omega = 2.0 * M_PI * f;
+    rc.cX = TORJ_E * TORJ_E / (TORJ_EPS0 * TORJ_ME * rc.omega * rc.omega);
+    rc.cY = TORJ_E / (TORJ_ME * rc.omega);
+    rc.w_over_c = rc.omega / TORJ_C;
+    rc.moded = (double)mode;
+    rc.mode = mode;
+    rc.te_min = te_min;
+    rc.max_harmonic = max_harmonic;
+    return rc;
+}
+
+struct Counters {
+    unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm;
+};
+
+// ------------------------------------------------------------------------------------------------
+// cubic B-spline weights; dw already divided by the grid step
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bs_weights(double d, double inv_h, double w[4], double dw[4]) {
+    double e = 1.0 - d;
+    double d2 = d * d, e2 = e * e;
+    w[0] = e2 * e * (1.0 / 6.0);
+    w[1] = 2.0 / 3.0 - d2 + 0.5 * d2 * d;
+    w[2] = 2.0 / 3.0 - e2 + 0.5 * e2 * e;
+    w[3] = d2 * d * (1.0 / 6.0);
+    dw[0] = -0.5 * e2 * inv_h;
+    dw[1] = (1.5 * d2 - 2.0 * d) * inv_h;
+    dw[2] = (2.0 * e - 1.5 * e2) * inv_h;
+    dw[3] = 0.5 * d2 * inv_h;
+}
+
+__device__ __forceinline__ int bs_locate(double x, double x0, double inv_h, int n, double w[4], double dw[4]) {
+    double u = (x - x0) * inv_h + 1.0;
+    int i = (int)floor(u);
+    i = min(max(i, 1), n - 1);
+    bs_weights(u - (double)i, inv_h, w, dw);
+    return i - 1;
+}
+
+struct Fields {  // value, d/dR, d/dZ
+    double BR, BR_R, BR_Z;
+    double BZ, BZ_R, BZ_Z;
+    double Bp, Bp_R, Bp_Z;
+    double L, L_R, L_Z;  // ln n_e
+    double lnTe;
+};
+
+// all five RHS fields at a point inside the grid
+__device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f) {
+    double wr[4], dwr[4], wz[4], dwz[4];
+    int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
+    int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
+    double v[4] = {0, 0, 0, 0}, vR[4] = {0, 0, 0, 0}, vZ[4] = {0, 0, 0, 0};
+    double te = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        size_t node = (size_t)(bz + j) * T.row + br;
+        const double2* pa = T.A + 2 * node;
+        const double2* pb = T.B + node;
+        double a[4] = {0, 0, 0, 0}, aR[4] = {0, 0, 0, 0};
+        double at = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double2 q0 = __ldg(pa + 2 * i);
+            double2 q1 = __ldg(pa + 2 * i + 1);
+            double2 q2 = __ldg(pb + i);
+            a[0] = fma(wr[i], q0.x, a[0]); aR[0] = fma(dwr[i], q0.x, aR[0]);
+            a[1] = fma(wr[i], q0.y, a[1]); aR[1] = fma(dwr[i], q0.y, aR[1]);
+            a[2] = fma(wr[i], q1.x, a[2]); aR[2] = fma(dwr[i], q1.x, aR[2]);
+            a[3] = fma(wr[i], q1.y, a[3]); aR[3] = fma(dwr[i], q1.y, aR[3]);
+            at = fma(wr[i], q2.x, at);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = fma(wz[j], a[q], v[q]);
+            vR[q] = fma(wz[j], aR[q], vR[q]);
+            vZ[q] = fma(dwz[j], a[q], vZ[q]);
+        }
+        te = fma(wz[j], at, te);
+    }
+    f.BR = v[0]; f.BR_R = vR[0]; f.BR_Z = vZ[0];
+    f.BZ = v[1]; f.BZ_R = vR[1]; f.BZ_Z = vZ[1];
+    f.Bp = v[2]; f.Bp_R = vR[2]; f.Bp_Z = vZ[2];
+    f.L = v[3]; f.L_R = vR[3]; f.L_Z = vZ[3];
+    f.lnTe = te;
+}
+
+// one field (0..3 from tabA, 4 = lnTe, 5 = psi) with value, gradient and mixed derivative, any position:
+// "Line" extrapolation  v = itp(xc) + sum_d (x_d - xc_d) g_d(xc)  and the gradient of that expression
+__device__ __noinline__ void eval_field_ext(const DevTables& T, int field, double R, double Z, double* val, double* dR,
+                                            double* dZ) {
+    double Rc = fmin(fmax(R, T.r0), T.rlast), Zc = fmin(fmax(Z, T.z0), T.zlast);
+    double wr[4], dwr[4], wz[4], dwz[4];
+    int br = bs_locate(Rc, T.r0, T.inv_hr, T.nR, wr, dwr);
+    int bz = bs_locate(Zc, T.z0, T.inv_hz, T.nZ, wz, dwz);
+    double s = 0, sR = 0, sZ = 0, sRZ = 0;
+    for (int j = 0; j < 4; ++j) {
+        double a = 0, aR = 0;
+        for (int i = 0; i < 4; ++i) {
+            size_t node = (size_t)(bz + j) * T.row + br + i;
+            double c;
+            if (field < 4) {
+                double2 q = __ldg(T.A + 2 * node + (field >> 1));
+                c = (field & 1) ? q.y : q.x;
+            } else {
+                double2 q = __ldg(T.B + node);
+                c = (field == 4) ? q.x : q.y;
+            }
+            a = fma(wr[i], c, a);
+            aR = fma(dwr[i], c, aR);
+        }
+        s = fma(wz[j], a, s); sR = fma(wz[j], aR, sR); sZ = fma(dwz[j], a, sZ); sRZ = fma(dwz[j], aR, sRZ);
+    }
+    bool outR = (Rc != R), outZ = (Zc != Z);
+    double v = s, vR = sR, vZ = sZ;
+    if (outR) { v += (R - Rc) * sR; if (!outZ) vZ += (R - Rc) * sRZ; }
+    if (outZ) { v += (Z - Zc) * sZ; if (!outR) vR += (Z - Zc) * sRZ; }
+    *val = v; *dR = vR; *dZ = vZ;
+}
+
+__device__ __forceinline__ bool inside_grid(const DevTables& T, double R, double Z) {
+    return R >= T.r0 && R <= T.rlast && Z >= T.z0 && Z <= T.zlast;
+}
+
+__device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f) {
+    if (inside_grid(T, R, Z)) {
+        eval_fields_in(T, R, Z, f);
+    } else {
+        double d0, d1;
+        eval_field_ext(T, 0, R, Z, &f.BR, &f.BR_R, &f.BR_Z);
+        eval_field_ext(T, 1, R, Z, &f.BZ, &f.BZ_R, &f.BZ_Z);
+        eval_field_ext(T, 2, R, Z, &f.Bp, &f.Bp_R, &f.Bp_Z);
+        eval_field_ext(T, 3, R, Z, &f.L, &f.L_R, &f.L_Z);
+        eval_field_ext(T, 4, R, Z, &f.lnTe, &d0, &d1);
+    }
+}
+
+// psi_N with gradient (reference src/plasma.jl:61-65 on psi_norm_spline; src/solve.jl:63)
+__device__ __forceinline__ void eval_psi(const DevTables& T, double R, double Z, double* psi, double* pR, double* pZ) {
+    if (!inside_grid(T, R, Z)) {
+        eval_field_ext(T, 5, R, Z, psi, pR, pZ);
+        return;
+    }
+    double wr[4], dwr[4], wz[4], dwz[4];
+    int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
+    int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
+    double s = 0, sR = 0, sZ = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2* pb = T.B + (size_t)(bz + j) * T.row + br;
+        double a = 0, aR = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double c = __ldg(pb + i).y;
+            a = fma(wr[i], c, a);
+            aR = fma(dwr[i], c, aR);
+        }
+        s = fma(wz[j], a, s); sR = fma(wz[j], aR, sR); sZ = fma(dwz[j], a, sZ);
+    }
+    *psi = s; *pR = sR; *pZ = sZ;
+}
+
+__device__ __forceinline__ double psi_at(const DevTables& T, const double x[3]) {
+    double p, a, b;
+    eval_psi(T, sqrt(x[0] * x[0] + x[1] * x[1]), x[2], &p, &a, &b);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cold dispersion: reference src/dispersion.jl:21-32 with first derivatives
+// ------------------------------------------------------------------------------------------------
+struct Disp {
+    double Ns2, dX, dY, dNp;
+};
+
+template <bool DERIV>
+__device__ __forceinline__ Disp refractive_index_sq(double X, double Y, double Np, double moded) {
+    Disp o;
+    double Np2 = Np * Np, Y2 = Y * Y;
+    double om = 1.0 - Np2;
+    double iY2 = 1.0 / Y2;
+    double delta = om * om + 4.0 * Np2 * (1.0 - X) * iY2;
+    double S = sqrt(delta);
+    double D = 2.0 * (-1.0 + X + Y2);
+    double iD = 1.0 / D;
+    double G = 1.0 + moded * S + Np2;
+    double H = X * Y2;
+    o.Ns2 = 1.0 - X + G * iD * H;
+    if (DERIV) {
+        double hS = 0.5 / S;  // dS/d. = dDelta/d. * hS
+        double S_X = -4.0 * Np2 * iY2 * hS;
+        double S_Y = -8.0 * Np2 * (1.0 - X) * iY2 / Y * hS;
+        double S_N = (-4.0 * Np * om + 8.0 * Np * (1.0 - X) * iY2) * hS;
+        double GH_D2 = G * H * iD * iD;
+        o.dX = -1.0 + (moded * S_X * H + G * Y2) * iD - 2.0 * GH_D2;
+        o.dY = (moded * S_Y * H + 2.0 * G * X * Y) * iD - 4.0 * Y * GH_D2;
+        o.dNp = (moded * S_N + 2.0 * Np) * H * iD;
+    } else {
+        o.dX = o.dY = o.dNp = 0.0;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Albajar absorption: reference src/absorption.jl:10-64 (polarisation), :132-189 (harmonic integral), :191-226
+// ------------------------------------------------------------------------------------------------
+struct Pol {  // e = (ex, i*ey, ez) with ex, ey, ez real
+    double ex, ey, ez;
+};
+
+__device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, double ct, double st, int mode, Pol& e) {
+    e.ex = e.ey = e.ez = 0.0;
+    if (X >= 1.0) return 0.0;
+    double st2 = st * st, ct2 = ct * ct, Y2 = Y * Y;
+    double omX = 1.0 - X;
+    double rho = Y2 * st2 * st2 + 4.0 * omX * omX * ct2;
+    if (rho < 0.0) return 0.0;
+    rho = sqrt(rho);
+    double f = (2.0 * omX) / (2.0 * omX - Y2 * st2 - (double)mode * Y * rho);
+    double N = 1.0 - X * f;
+    if (N < 0.0) return 0.0;
+    N = sqrt(N);
+    double h = 1.0 - (1.0 - Y2) * f;
+    double g = h / Y;
+    if (ct2 < 1e-5 || 1.0 - st2 < 1e-5) {
+        if (mode > 0) {
+            e.ey = sqrt(1.0 / N);
+            e.ex = -g * e.ey;
+        } else {
+            e.ez = sqrt(1.0 / N);
+        }
+    } else {
+        double N2 = N * N;
+        double den = omX - N2 * st2;
+        double hy = h * h / Y2;
+        double a_in = 1.0 + ((omX * N2 * ct2) / (den * den)) * hy;
+        double a_sq = st2 * a_in * a_in;
+        double b_in = 1.0 + (omX / den) * hy;
+        double b_sq = ct2 * b_in * b_in;
+        double ey = sqrt(1.0 / (N * sqrt(a_sq + b_sq)));
+        e.ey = mode > 0 ? ey : -ey;
+        e.ex = -g * e.ey;                           // i*g * (i*ey)
+        e.ez = -((N2 * st * ct) / den) * e.ex;
+    }
+    return N;
+}
+
+// J_{M-1}, J_M, J_{M+1} at z given hz = z/2, y = hz^2, by K-term Horner series
+template <int M, int K>
+__device__ __forceinline__ void bessel3(double hz, double y, double& Jl, double& Jn, double& Ju) {
+    const double ny = y;  // series in +y, the alternating sign lives in the coefficients
+    double sl = c_bess[M - 1][K - 1], sn = c_bess[M][K - 1], su = c_bess[M + 1][K - 1];
+#pragma unroll
+    for (int k = K - 2; k >= 0; --k) {
+        sl = fma(sl, ny, c_bess[M - 1][k]);
+        sn = fma(sn, ny, c_bess[M][k]);
+        su = fma(su, ny, c_bess[M + 1][k]);
+    }
+    // (z/2)^n / n!
+    double p1 = hz, p2 = hz * hz * 0.5, p3 = p2 * hz * (1.0 / 3.0), p4 = p3 * hz * 0.25;
+    if (M == 2) { Jl = p1 * sl; Jn = p2 * sn; Ju = p3 * su; }
+    else        { Jl = p2 * sl; Jn = p3 * sn; Ju = p4 * su; }
+}
+
+struct HarmPre {  // per-call invariants of the harmonic integral
+    double mu, omega_bar, m_0, N_par, N_perp, spar;  // spar = sqrt(1 - N_par^2)
+    double Axz_sq_ey_sq, Re_Axz_ey, Re_Axz_ez, Re_ey_ez, ey_sq, ez_sq;
+};
+
+// reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M; returns c_abs_m
+template <int M, int K, bool GENERIC>
+__device__ __forceinline__ double harmonic_sum(const HarmPre& h, double x_m, double A /* M/m_0 */, double q /* sqrt(A^2-1) */) {
+    const double fm = (double)M;
+    // gamma is linear in t on the resonance curve: gamma = (A + N_par q t)/spar  (== sqrt(1+u_par^2+u_perp^2))
+    double g0 = A / h.spar, g1 = h.N_par * q / h.spar;
+    double e0 = h.mu * (1.0 - g0), e1 = -h.mu * g1;
+    double xs = x_m / (fm * h.spar);
+    double xm_m = x_m / fm;
+    double k1 = h.Axz_sq_ey_sq;
+    double k2 = h.Re_Axz_ey * xm_m;
+    double k3 = h.ey_sq / (fm * fm);
+    double k4 = xs * xs * h.ez_sq;
+    double k5 = 2.0 * xs * h.Re_Axz_ez;
+    double k6 = xs * h.Re_ey_ez * xm_m;
+    double sum = 0.0;
+    const int n = c_gl.n;
+#pragma unroll 2
+    for (int k = 0; k < n; ++k) {
+        double t = c_gl.t[k], sq = c_gl.sq[k];
+        double ex = exp(fma(e1, t, e0));
+        double z = x_m * sq;
+        double Jl, Jn, Ju;
+        if (GENERIC) {
+            Jl = jn(M - 1, z); Jn = jn(M, z); Ju = jn(M + 1, z);
+        } else {
+            double hz = 0.5 * z;
+            bessel3<M, K>(hz, hz * hz, Jl, Jn, Ju);
+        }
+        double Jn2 = Jn * Jn;
+        double dsq = sq * Jn * (Jl - Ju);
+        double pf = k1 * Jn2;
+        pf = fma(k2, dsq, pf);
+        pf = fma(-k3 * z * z, Jl * Ju, pf);
+        double tJ = t * Jn2;
+        pf = fma(k4 * t, tJ, pf);
+        pf = fma(k5, tJ, pf);
+        pf = fma(k6 * t, dsq, pf);
+        sum = fma(c_gl.w[k] * pf, ex, sum);
+    }
+    double sc = fm / (h.N_perp * h.omega_bar);
+    double a = 1.0 / (1.0 + 105.0 / (128.0 * h.mu * h.mu) + 15.0 / (8.0 * h.mu));
+    double s = sqrt(h.mu * (0.5 / M_PI));
+    return sum * (-h.mu) * sc * sc * a * (s * s * s);
+}
+
+// rarely taken variants kept out of line so the hot code stays small (instruction cache)
+template <int M>
+__device__ __noinline__ double harmonic_sum_large(const HarmPre& h, double x_m, double A, double q) {
+    if (x_m <= 6.5) return harmonic_sum<M, 24, false>(h, x_m, A, q);
+    return harmonic_sum<M, 1, true>(h, x_m, A, q);
+}
+
+// Series length: |term_K| = y^K n!/(K!(n+K)!) with y = x_m^2/4; K=14 is below 1e-17 for x_m <= 3.2
+// (covers the m=2 layer, x_m ~ 1, and m=3 next to it, x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
+template <int M>
+__device__ __forceinline__ double harmonic_integral(const HarmPre& h) {
+    const double fm = (double)M;
+    double A = fm / h.m_0;
+    double q = sqrt(A * A - 1.0);
+    double x_m = h.N_perp * h.omega_bar * q;
+    double c;
+    if (x_m <= 3.2) c = harmonic_sum<M, 14, false>(h, x_m, A, q);
+    else c = harmonic_sum_large<M>(h, x_m, A, q);
+    return q * c;  // sqrt((m/m_0)^2 - 1) * c_abs_m, reference src/absorption.jl:218
+}
+
+// reference src/absorption.jl:191-226; omega enters only through omega/c
+__device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double N_abs, double N_par, double Te,
+                                              Counters& cnt) {
+    if (Te < rc.te_min) return 0.0;
+    cnt.n_alpha++;
+    HarmPre h;
+    h.mu = TORJ_ME * TORJ_C * TORJ_C / (TORJ_E * Te);
+    h.omega_bar = 1.0 / Y;
+    double ct = N_par / N_abs;
+    double st = sqrt(fmax(0.0, (1.0 - ct) * (1.0 + ct)));  // sin(acos(ct))
+    h.N_perp = sqrt(N_abs * N_abs - N_par * N_par);
+    h.N_par = N_par;
+    Pol e;
+    double N_test = abs_Al_N_with_pol_vec(X, Y, ct, st, rc.mode, e);
+    if (!(N_test > 0.0) || N_test > 1.0) return 0.0;  // also catches NaN
+    h.spar = sqrt(1.0 - N_par * N_par);
+    h.m_0 = h.spar * h.omega_bar;
+    double N_eff = (h.N_perp * N_par) / (1.0 - N_par * N_par);
+    double Axz = e.ex + N_eff * e.ez;
+    h.ey_sq = e.ey * e.ey;
+    h.ez_sq = e.ez * e.ez;
+    h.Axz_sq_ey_sq = Axz * Axz + h.ey_sq;
+    h.Re_Axz_ey = Axz * e.ey;
+    h.Re_Axz_ez = Axz * e.ez;
+    h.Re_ey_ez = e.ey * e.ez;
+    double c_abs = 0.0;
+    if (2.0 >= h.m_0 && rc.max_harmonic >= 2) { cnt.n_harm++; c_abs += harmonic_integral<2>(h); }
+    if (3.0 >= h.m_0 && rc.max_harmonic >= 3) { cnt.n_harm++; c_abs += harmonic_integral<3>(h); }
+    c_abs = -(c_abs * 2.0 * M_PI * M_PI / h.m_0);
+    return c_abs * X * rc.w_over_c / Y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hamiltonian RHS: reference src/solve.jl:85-95 (gradΛ!) with analytic gradients
+// ------------------------------------------------------------------------------------------------
+struct PointVals {
+    double X, Y, N_par, b[3], Te, Lambda;
+};
+
+template <bool WITH_ALPHA>
+__device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
+                                    PointVals* pv = nullptr) {
+    const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
+    double R = sqrt(fma(x, x, y * y));
+    double iR = 1.0 / R;
+    double c = x * iR, s = y * iR;
+    Fields f;
+    eval_fields(T, R, z, f);
+    double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
+    double Babs = sqrt(B2);
+    double iB = 1.0 / Babs;
+    double NR = Nx * c + Ny * s, Nph = -Nx * s + Ny * c;
+    double NB = NR * f.BR + Nph * f.Bp + Nz * f.BZ;
+    double Np = NB * iB;
+    double bx = (f.BR * c - f.Bp * s) * iB, by = (f.BR * s + f.Bp * c) * iB, bz = f.BZ * iB;
+    double X = rc.cX * exp(f.L);
+    double Y = rc.cY * Babs;
+    Disp d = refractive_index_sq<true>(X, Y, Np, rc.moded);
+    // cylindrical gradients of X, Y, N_par at fixed N
+    double X_R = X * f.L_R, X_Z = X * f.L_Z;
+    double Bab_R = (f.BR * f.BR_R + f.Bp * f.Bp_R + f.BZ * f.BZ_R) * iB;
+    double Bab_Z = (f.BR * f.BR_Z + f.Bp * f.Bp_Z + f.BZ * f.BZ_Z) * iB;
+    double Y_R = rc.cY * Bab_R, Y_Z = rc.cY * Bab_Z;
+    double NB_R = NR * f.BR_R + Nph * f.Bp_R + Nz * f.BZ_R;
+    double NB_Z = NR * f.BR_Z + Nph * f.Bp_Z + Nz * f.BZ_Z;
+    double Np_R = (NB_R - Np * Bab_R) * iB;
+    double Np_Z = (NB_Z - Np * Bab_Z) * iB;
+    double Np_ph = (Nph * f.BR - NR * f.Bp) * iB;
+    double gR = -(d.dX * X_R + d.dY * Y_R + d.dNp * Np_R);
+    double gZ = -(d.dX * X_Z + d.dY * Y_Z + d.dNp * Np_Z);
+    double gph = -(d.dNp * Np_ph) * iR;
+    double gx = c * gR - s * gph, gy = s * gR + c * gph, gz = gZ;
+    double hx = 2.0 * Nx - bx * d.dNp, hy = 2.0 * Ny - by * d.dNp, hz = 2.0 * Nz - bz * d.dNp;
+    double inorm = 1.0 / sqrt(hx * hx + hy * hy + hz * hz);
+    du[0] = hx * inorm; du[1] = hy * inorm; du[2] = hz * inorm;
+    du[3] = -gx * inorm; du[4] = -gy * inorm; du[5] = -gz * inorm;
+    double N2 = Nx * Nx + Ny * Ny + Nz * Nz;
+    if (WITH_ALPHA) {
+        double Te = exp(f.lnTe);
+        double alpha = abs_albajar(rc, X, Y, sqrt(N2), Np, Te, cnt);
+        du[6] = -u[6] * alpha;
+        if (pv) pv->Te = Te;
+    } else {
+        du[6] = 0.0;
+    }
+    cnt.n_rhs++;
+    if (pv) {
+        pv->X = X; pv->Y = Y; pv->N_par = Np; pv->b[0] = bx; pv->b[1] = by; pv->b[2] = bz;
+        pv->Lambda = N2 - d.Ns2;
+    }
+}
+
+// single out-of-line copy for the integrator: every stage of every step calls this one body
+__device__ __noinline__ void rhs_call(const DevTables* __restrict__ Tp, const RayConst* rcp, const double* u, double* du,
+                                      Counters* cnt) {
+    DevTables T = *Tp;
+    rhs<true>(T, *rcp, u, du, *cnt);
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming psi-shell deposition (algorithm shared with oracle/deposition.hpp: deposition_streaming)
+// ------------------------------------------------------------------------------------------------
+struct DepoState {
+    int shell;      // psi_grid[shell] <= psi < psi_grid[shell+1]; -1 below all levels, n_psi-1 above all
+    int valid;      // a crossing has been seen
+    double P_last;  // P at the last crossing
+};
+
+__device__ __forceinline__ int locate_shell(const double* g, int n, double psi) {  // upper_bound(psi) - 1
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (g[mid] <= psi) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
+__device__ __forceinline__ double hermite(double f0, double f1, double d0, double d1, double h, double th) {
+    double t2 = th * th, t3 = t2 * th;
+    return (2 * t3 - 3 * t2 + 1) * f0 + (t3 - 2 * t2 + th) * h * d0 + (-2 * t3 + 3 * t2) * f1 + (t3 - t2) * h * d1;
+}
+__device__ __forceinline__ double hermite_d(double f0, double f1, double d0, double d1, double h, double th) {
+    double t2 = th * th;
+    return (6 * t2 - 6 * th) * f0 + (3 * t2 - 4 * th + 1) * h * d0 + (-6 * t2 + 6 * th) * f1 + (3 * t2 - 2 * th) * h * d1;
+}
+
+// Deposit callback: sink(shell, dP)
+template <class Sink>
+__device__ __forceinline__ void depo_step(DepoState& st, const double* g, int npsi, double h, double psi_a, double psi_b,
+                                          double dpsi_a, double dpsi_b, double P_a, double P_b, double dP_a, double dP_b,
+                                          Sink&& sink) {
+    while (true) {
+        int lvl, nshell;
+        if (psi_b < psi_a) {
+            lvl = st.shell;
+            if (lvl < 0 || !(psi_b < g[lvl])) return;
+            nshell = lvl - 1;
+        } else {
+            lvl = st.shell + 1;
+            if (lvl > npsi - 1 || !(psi_b >= g[lvl])) return;
+            nshell = lvl;
+        }
+        double gl = g[lvl];
+        double th = (gl - psi_a) / (psi_b - psi_a);
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            double f = hermite(psi_a, psi_b, dpsi_a, dpsi_b, h, th) - gl;
+            double d = hermite_d(psi_a, psi_b, dpsi_a, dpsi_b, h, th);
+            if (d != 0.0) th -= f / d;
+            th = fmin(1.0, fmax(0.0, th));
+        }
+        double Pc = hermite(P_a, P_b, dP_a, dP_b, h, th);
+        if (st.valid && st.shell >= 0 && st.shell < npsi - 1) sink(st.shell, fabs(st.P_last - Pc));
+        st.P_last = Pc;
+        st.valid = 1;
+        st.shell = nshell;
+    }
+}
+
+}  // namespace torj

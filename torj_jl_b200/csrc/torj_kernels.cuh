@@ -1,0 +1,582 @@
+// Kernels of libtorj_cuda.so (sm_100a).
+//   k_ray_init : first_point + vacuum_plasma_refraction, one thread per ray   (reference src/solve.jl:18-74,137-144)
+//   k_trace    : persistent one-thread-per-ray integrator with warp-ballot retire-and-refill of finished rays,
+//                streaming psi-shell deposition into shared-memory bins       (reference src/solve.jl:154-177, src/plasma.jl:91-151)
+//   k_finalize : bins / dV -> dP_dV                                            (reference src/plasma.jl:141, src/solve.jl:233-240)
+//   k_probe, k_rhs : point probes for parity tests; k_dfma : FP64 peak microbenchmark
+#pragma once
+#include "torj_device.cuh"
+
+namespace torj {
+
+// Runge-Kutta tableaux (OrdinaryDiffEq Tsit5 / OwrenZen3), uploaded once per context
+struct Tableau {
+    double a[7][7];
+    double bt[7];
+};
+__constant__ Tableau c_tab[2];
+
+struct SolverOpts {
+    int n_segments;
+    int max_steps;
+    double s_max, dtmax, abstol, reltol, psi_stop, p_stop, te_min;
+    int max_harmonic;
+};
+
+struct BundleDev {
+    long long n_rays;
+    const double* pos;     // [3][n] launch positions
+    const double* dir;     // [3][n] vacuum directions
+    const double* weight;  // [n]
+    const double* freq;    // [n] or [1]
+    const int* mode;       // [n] or [1]
+    int per_ray_fm;
+    double* u0;            // [7][n] state at plasma entry
+    double* s0;            // [n] vacuum path length
+    double* psi_launch;    // [n]
+    int* status;           // [n]
+    double* P_final;       // [n]
+    double* P_dep;         // [n] profile-integrated deposited power of the ray
+    int* n_points;         // [n]
+};
+
+struct TrajDev {
+    long long first, count;
+    int max_pts;
+    double *s, *xyz, *P, *dP, *prof;  // [count][max], [count][3][max], [count][max], [count][max], [count][n_psi]
+};
+
+// ------------------------------------------------------------------------------------------------
+// ray initialisation
+// ------------------------------------------------------------------------------------------------
+__device__ inline bool box_intersection(const DevTables& T, const double p0[3], const double N0[3], double* t_out) {
+    double best = INFINITY;
+    const double tiny = 1e-12;
+    double a = N0[0] * N0[0] + N0[1] * N0[1];
+    double b = 2.0 * (p0[0] * N0[0] + p0[1] * N0[1]);
+    for (int k = 0; k < 2; ++k) {
+        double Rc = k == 0 ? T.r0 : T.rlast;
+        double c = p0[0] * p0[0] + p0[1] * p0[1] - Rc * Rc;
+        if (a <= 0.0) continue;
+        double disc = b * b - 4.0 * a * c;
+        if (disc < 0.0) continue;
+        double sq = sqrt(disc);
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            double t = (-b + sgn * sq) / (2.0 * a);
+            if (t <= tiny) continue;
+            double z = p0[2] + t * N0[2];
+            if (z >= T.z0 && z <= T.zlast && t < best) best = t;
+        }
+    }
+    if (N0[2] != 0.0) {
+        for (int k = 0; k < 2; ++k) {
+            double Zc = k == 0 ? T.z0 : T.zlast;
+            double t = (Zc - p0[2]) / N0[2];
+            if (t <= tiny) continue;
+            double R = hypot(p0[0] + t * N0[0], p0[1] + t * N0[1]);
+            if (R >= T.r0 && R <= T.rlast && t < best) best = t;
+        }
+    }
+    if (!isfinite(best)) return false;
+    *t_out = best;
+    return true;
+}
+
+// 3x3 solve with complete pivoting; pivots below 1e-14*scale are skipped (their unknown stays 0): the
+// minimum-norm answer for the zero row+column of the tor=0 central ray
+__device__ inline void solve3_robust(double A[3][3], double rhs[3], double x[3]) {
+    int rp[3] = {0, 1, 2}, cp[3] = {0, 1, 2};
+    int rank = 0;
+    double scale = 0.0;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) scale = fmax(scale, fabs(A[i][j]));
+    for (int k = 0; k < 3; ++k) {
+        int pi = k, pj = k; double best = 0.0;
+        for (int i = k; i < 3; ++i) for (int j = k; j < 3; ++j) {
+            double v = fabs(A[rp[i]][cp[j]]);
+            if (v > best) { best = v; pi = i; pj = j; }
+        }
+        if (best <= 1e-14 * scale) break;
+        int t = rp[k]; rp[k] = rp[pi]; rp[pi] = t;
+        t = cp[k]; cp[k] = cp[pj]; cp[pj] = t;
+        for (int i = k + 1; i < 3; ++i) {
+            double f = A[rp[i]][cp[k]] / A[rp[k]][cp[k]];
+            for (int j = k; j < 3; ++j) A[rp[i]][cp[j]] -= f * A[rp[k]][cp[j]];
+            rhs[rp[i]] -= f * rhs[rp[k]];
+        }
+        rank = k + 1;
+    }
+    x[0] = x[1] = x[2] = 0.0;
+    for (int k = rank - 1; k >= 0; --k) {
+        double s = rhs[rp[k]];
+        for (int j = k + 1; j < rank; ++j) s -= A[rp[k]][cp[j]] * x[cp[j]];
+        x[cp[k]] = s / A[rp[k]][cp[k]];
+    }
+}
+
+// reference src/solve.jl:40-49; J (if non-null) is the analytic Jacobian of F_k = W_k^2 - N_k^2,
+// W_k = n0_k + (ndN - sqrt(Ns^2 - 1 + ndN^2)) n_k
+__device__ inline void refraction_equations(const double N[3], double X, double Y, const double n0[3], const double n[3],
+                                            const double b[3], double moded, double F[3], double (*J)[3]) {
+    double ndN = -(n[0] * n0[0] + n[1] * n0[1] + n[2] * n0[2]);
+    double Np = N[0] * b[0] + N[1] * b[1] + N[2] * b[2];
+    Disp d = refractive_index_sq<true>(X, Y, Np, moded);
+    double Ns = sqrt(d.Ns2);
+    double coef = 1.0 / Ns * ndN - sqrt(1.0 - 1.0 / (Ns * Ns) * (1.0 - ndN * ndN));
+    for (int k = 0; k < 3; ++k) {
+        double Fk = n0[k] / Ns + coef * n[k];
+        F[k] = Fk * Fk * (Ns * Ns) - N[k] * N[k];
+    }
+    if (J) {
+        double root = sqrt(d.Ns2 - 1.0 + ndN * ndN);
+        double c2 = ndN - root;
+        for (int k = 0; k < 3; ++k) {
+            double W = n0[k] + c2 * n[k];
+            double dW = -n[k] / (2.0 * root);
+            for (int j = 0; j < 3; ++j) J[k][j] = 2.0 * W * dW * d.dNp * b[j] - (k == j ? 2.0 * N[k] : 0.0);
+        }
+    }
+}
+
+__global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_rays) return;
+    const long long n = B.n_rays;
+    double x0[3] = {B.pos[i], B.pos[n + i], B.pos[2 * n + i]};
+    double N0[3] = {B.dir[i], B.dir[n + i], B.dir[2 * n + i]};
+    double f = B.per_ray_fm ? B.freq[i] : B.freq[0];
+    int mode = B.per_ray_fm ? B.mode[i] : B.mode[0];
+    RayConst rc = make_ray_const(f, mode, O.te_min, O.max_harmonic);
+    int status = 0;
+    B.P_final[i] = 0.0; B.P_dep[i] = 0.0; B.n_points[i] = 0;
+    B.psi_launch[i] = psi_at(T, x0);
+
+    // ---- first_point (reference src/solve.jl:18-38)
+    double p[3] = {x0[0], x0[1], x0[2]};
+    {
+        double R = sqrt(x0[0] * x0[0] + x0[1] * x0[1]);
+        if (!inside_grid(T, R, x0[2])) {
+            double t;
+            if (!box_intersection(T, x0, N0, &t)) { B.status[i] = 2; return; }
+            for (int k = 0; k < 3; ++k) p[k] = x0[k] + N0[k] * t;
+        }
+    }
+    {
+        auto g = [&](double t) {
+            double xx[3] = {p[0] + t * N0[0], p[1] + t * N0[1], p[2] + t * N0[2]};
+            return psi_at(T, xx) - T.psi_prof_max;
+        };
+        double a = 0.0, b = 0.5;
+        double ga = g(a), gb = g(b), root;
+        if (ga == 0.0) root = a;
+        else if (gb == 0.0) root = b;
+        else {
+            if ((ga < 0.0) == (gb < 0.0)) { B.status[i] = 2; return; }
+            for (int it = 0; it < 200; ++it) {
+                double m = 0.5 * (a + b);
+                if (m <= a || m >= b) break;
+                double gm = g(m);
+                if (gm == 0.0) { a = b = m; ga = gb = 0.0; break; }
+                if ((gm < 0.0) == (ga < 0.0)) { a = m; ga = gm; } else { b = m; gb = gm; }
+            }
+            root = (ga <= 0.0) ? a : b;  // the end with psi <= psi_prof_max (assert src/solve.jl:138)
+        }
+        for (int k = 0; k < 3; ++k) p[k] += root * N0[k];
+        double psi_ref = psi_at(T, p);
+        if (!(fabs(psi_ref - T.psi_prof_max) < 1e-6)) { B.status[i] = 2; return; }
+        if (psi_ref > T.psi_prof_max)
+            for (int k = 0; k < 3; ++k) p[k] += 2.0 * (psi_ref - T.psi_prof_max) * N0[k];
+        if (!(psi_at(T, p) <= T.psi_prof_max)) { B.status[i] = 2; return; }
+    }
+    // ---- vacuum_plasma_refraction (reference src/solve.jl:51-74)
+    double Np[3];
+    {
+        double u[7] = {p[0], p[1], p[2], N0[0], N0[1], N0[2], 1.0}, du[7];
+        Counters c0 = {0, 0, 0, 0, 0};
+        PointVals pv;
+        rhs<false>(T, rc, u, du, c0, &pv);
+        Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 0.0, rc.moded);
+        if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; return; }
+        double N_est = sqrt(d0.Ns2);
+        double R = sqrt(p[0] * p[0] + p[1] * p[1]);
+        double psi, pR, pZ;
+        eval_psi(T, R, p[2], &psi, &pR, &pZ);
+        double nv[3] = {pR * p[0] / R, pR * p[1] / R, pZ};
+        double nn = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+        for (int k = 0; k < 3; ++k) nv[k] /= nn;
+        double n0n = sqrt(N0[0] * N0[0] + N0[1] * N0[1] + N0[2] * N0[2]);
+        double n0[3] = {N0[0] / n0n, N0[1] / n0n, N0[2] / n0n};
+        double N[3] = {N0[0] * N_est, N0[1] * N_est, N0[2] * N_est};
+        bool ok = false;
+        for (int it = 0; it < 50 && status == 0; ++it) {
+            double F[3], J[3][3];
+            refraction_equations(N, pv.X, pv.Y, n0, nv, pv.b, rc.moded, F, J);
+            double fn = fmax(fabs(F[0]), fmax(fabs(F[1]), fabs(F[2])));
+            if (!(fn == fn)) { status = 2; break; }
+            if (fn < 1e-12) { ok = true; break; }
+            double r[3] = {-F[0], -F[1], -F[2]}, dx[3];
+            solve3_robust(J, r, dx);
+            double lam = 1.0, f2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+            bool stepped = false;
+            for (int ls = 0; ls < 30; ++ls) {
+                double Nt[3] = {N[0] + lam * dx[0], N[1] + lam * dx[1], N[2] + lam * dx[2]}, Ft[3];
+                refraction_equations(Nt, pv.X, pv.Y, n0, nv, pv.b, rc.moded, Ft, nullptr);
+                double f2t = Ft[0] * Ft[0] + Ft[1] * Ft[1] + Ft[2] * Ft[2];
+                if (f2t == f2t && f2t < f2) { for (int k = 0; k < 3; ++k) N[k] = Nt[k]; stepped = true; break; }
+                lam *= 0.5;
+            }
+            if (!stepped) { status = 2; break; }
+        }
+        if (!ok && status == 0) status = 2;
+        if (status != 0) { B.status[i] = status; return; }
+        for (int k = 0; k < 3; ++k) Np[k] = N[k];
+        // assert |Λ| < 1e-12 (reference src/solve.jl:141)
+        double u2[7] = {p[0], p[1], p[2], Np[0], Np[1], Np[2], 1.0};
+        rhs<false>(T, rc, u2, du, c0, &pv);
+        // Λ as the reference forms it: norm(N)^2 - Ns^2
+        if (!(fabs(pv.Lambda) < 1e-12)) { B.status[i] = 2; return; }
+    }
+    B.u0[i] = p[0]; B.u0[n + i] = p[1]; B.u0[2 * n + i] = p[2];
+    B.u0[3 * n + i] = Np[0]; B.u0[4 * n + i] = Np[1]; B.u0[5 * n + i] = Np[2];
+    B.u0[6 * n + i] = 1.0;
+    double dx0 = p[0] - x0[0], dx1 = p[1] - x0[1], dx2 = p[2] - x0[2];
+    B.s0[i] = sqrt(dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+    B.status[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trace kernel
+// ------------------------------------------------------------------------------------------------
+struct TraceArgs {
+    DevTables T;
+    const DevTables* Tg;  // the same tables descriptor in global memory (for the out-of-line RHS)
+    BundleDev B;
+    SolverOpts O;
+    TrajDev J;
+    int n_psi;
+    const double* psi_edges;          // [n_psi]
+    double* bins;                     // [n_psi] weighted shell power, [n_psi] = sum w_i P_i, [n_psi+1] = sum w_i
+    unsigned long long* next_ray;     // work queue head
+    unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok
+};
+
+__device__ __forceinline__ double eps_of(double x) {  // Julia eps(x)
+    x = fabs(x);
+    return __longlong_as_double(__double_as_longlong(x) + 1) - x;
+}
+
+__device__ __forceinline__ double rms7(const double v[7]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) s = fma(v[i], v[i], s);
+    return sqrt(s / 7.0);
+}
+
+template <int SCH>
+struct Scheme;
+template <> struct Scheme<0> { static constexpr int S = 7; static constexpr int ORDER = 5; };
+template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int ORDER = 3; };
+
+#define TORJ_TPB 128
+// per-ray status codes of include/torj_cuda.h: everything but OK(0) and TRAJ_TRUNCATED(6) ends the ray
+#define TORJ_FATAL(s) ((s) != 0 && (s) != 6)
+
+template <int SCH>
+__global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
+    constexpr int S = Scheme<SCH>::S;
+    constexpr int ORDER = Scheme<SCH>::ORDER;
+    extern __shared__ double smem[];
+    double* s_edges = smem;             // [n_psi]
+    double* s_bins = smem + a.n_psi;    // [n_psi]
+    __shared__ unsigned long long s_cnt[6];
+    __shared__ double s_tot[2];
+    const int n_psi = a.n_psi;
+    for (int j = threadIdx.x; j < n_psi; j += blockDim.x) { s_edges[j] = a.psi_edges[j]; s_bins[j] = 0.0; }
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    const DevTables& T = a.T;
+    const SolverOpts& O = a.O;
+    const long long n = a.B.n_rays;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    const Tableau& tb = c_tab[SCH];
+    const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
+    const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
+    const double s_step = O.s_max / (double)O.n_segments;
+
+    // per-lane ray state
+    long long ray = -1;  // -1: needs a ray, -2: queue exhausted
+    double u[7], k[S][7];
+    double s0 = 0.0, wgt = 0.0, pdep = 0.0;
+    double psi_cur = 0.0, dpsi_cur = 0.0;
+    int seg = 0, npts = 0, rstat = 0;
+    RayConst rc;
+    DepoState dst;
+    Counters cnt = {0, 0, 0, 0, 0};
+    double tot_dep = 0.0, tot_w = 0.0;
+    unsigned int rays_ok = 0;
+    long long tj = -1;  // index into the trajectory window or -1
+
+    auto sink = [&](int shell, double dP) {
+        atomicAdd(&s_bins[shell], wgt * dP);
+        pdep += dP;
+        if (tj >= 0) a.J.prof[tj * n_psi + shell] += dP;
+    };
+    auto put_point = [&](double s, const double* xx, double P, double dP) {
+        if (tj >= 0) {
+            if (npts < a.J.max_pts) {
+                size_t o = (size_t)tj * a.J.max_pts + npts;
+                a.J.s[o] = s; a.J.P[o] = P; a.J.dP[o] = dP;
+                size_t ox = (size_t)tj * 3 * a.J.max_pts + npts;
+                a.J.xyz[ox] = xx[0]; a.J.xyz[ox + a.J.max_pts] = xx[1]; a.J.xyz[ox + 2 * (size_t)a.J.max_pts] = xx[2];
+            } else if (rstat == 0) {
+                rstat = 6;  // TORJ_RAY_TRAJ_TRUNCATED
+            }
+        }
+        npts++;
+    };
+
+    for (;;) {
+        // ---- warp-ballot retire-and-refill: lanes without a ray draw the next indices from the global queue
+        unsigned need = __ballot_sync(FULL, ray == -1);
+        if (need) {
+            int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.next_ray, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (ray == -1) {
+                long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (idx >= n) {
+                    ray = -2;
+                } else if (a.B.status[idx] != 0) {
+                    ray = -1;  // init failed: outputs already written by k_ray_init; draw again next round
+                } else {
+                    ray = idx;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) u[i] = a.B.u0[(size_t)i * n + idx];
+                    s0 = a.B.s0[idx];
+                    wgt = a.B.weight[idx];
+                    double f = a.B.per_ray_fm ? a.B.freq[idx] : a.B.freq[0];
+                    int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
+                    rc = make_ray_const(f, mode, O.te_min, O.max_harmonic);
+                    seg = 0; npts = 0; rstat = 0; pdep = 0.0;
+                    tj = (idx >= a.J.first && idx < a.J.first + a.J.count) ? idx - a.J.first : -1;
+                    // samples 1 and 2: launch point and plasma entry (reference src/solve.jl:149-153)
+                    double xl[3] = {a.B.pos[idx], a.B.pos[n + idx], a.B.pos[2 * n + idx]};
+                    put_point(0.0, xl, 1.0, 0.0);
+                    put_point(s0, u, 1.0, 0.0);
+                    // derivative at entry (FSAL seed) and psi there
+                    rhs_call(a.Tg, &rc, u, k[0], &cnt);
+                    double R = sqrt(u[0] * u[0] + u[1] * u[1]), pR, pZ;
+                    eval_psi(T, R, u[2], &psi_cur, &pR, &pZ);
+                    dpsi_cur = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
+                    // vacuum leg launch -> entry: P = 1, straight line
+                    double psl = a.B.psi_launch[idx];
+                    dst.shell = locate_shell(s_edges, n_psi, psl);
+                    dst.valid = 0; dst.P_last = 1.0;
+                    double dlin = (psi_cur - psl) / s0;
+                    depo_step(dst, s_edges, n_psi, s0, psl, psi_cur, dlin, dlin, 1.0, 1.0, 0.0, 0.0, sink);
+                }
+            }
+        }
+        if (__all_sync(FULL, ray == -2)) break;
+        const bool act = ray >= 0;
+
+        // ---- one segment = one fresh ODEProblem of the reference (src/solve.jl:155-161)
+        double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit;
+        int nstep = 0;
+        if (act) {
+            seg++;
+            t = (double)(seg - 1) * s_step + s0;
+            tstop = (double)seg * s_step + s0;
+            // initial dt: OrdinaryDiffEq ode_determine_initdt (Hairer); k[0] = f(u) is the FSAL derivative
+            double sk[7], v0[7], v1[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { sk[i] = O.abstol + fabs(u[i]) * O.reltol; v0[i] = u[i] / sk[i]; v1[i] = k[0][i] / sk[i]; }
+            double d0 = rms7(v0), d1 = rms7(v1);
+            const double smalldt = 1e-6;
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
+            dt0 = fmin(dt0, O.dtmax);
+            if (dt0 < 10.0 * 2.220446049250313e-16) {
+                dt = smalldt;
+            } else {
+                double u1[7], f1[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) u1[i] = u[i] + dt0 * k[0][i];
+                rhs_call(a.Tg, &rc, u1, f1, &cnt);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) v0[i] = (f1[i] - k[0][i]) / sk[i];
+                double d2 = rms7(v0) / dt0;
+                double md = fmax(d1, d2);
+                double dt1 = (md <= 1e-15) ? fmax(smalldt, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / (double)ORDER);
+                dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
+            }
+        }
+        // ---- step loop, warp-uniform trip count so lanes reconverge every step
+        while (__any_sync(FULL, act && !TORJ_FATAL(rstat) && t < tstop)) {
+            if (act && !TORJ_FATAL(rstat) && t < tstop) {
+                if (++nstep > O.max_steps) { rstat = 4;  // TORJ_RAY_MAX_STEPS
+                    continue; }
+                dt = fmin(dt, tstop - t);
+                double tmp[7];
+#pragma unroll
+                for (int st = 1; st < S; ++st) {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < st; ++j) acc = fma(tb.a[st][j], k[j][i], acc);
+                        tmp[i] = fma(dt, acc, u[i]);
+                    }
+                    rhs_call(a.Tg, &rc, tmp, k[st], &cnt);
+                }
+                double at[7];
+                bool bad = false;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    double ut = 0.0;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) ut = fma(tb.bt[j], k[j][i], ut);
+                    ut *= dt;
+                    at[i] = ut / (O.abstol + fmax(fabs(u[i]), fabs(tmp[i])) * O.reltol);
+                    if (!(tmp[i] == tmp[i])) bad = true;
+                }
+                if (bad) { rstat = 5;  // TORJ_RAY_NAN
+                    continue; }
+                double EEst = rms7(at);
+                double qq, q11 = 0.0;
+                if (EEst == 0.0) qq = 1.0 / qmax;
+                else {
+                    q11 = pow(EEst, beta1);
+                    qq = q11 / pow(qold, beta2);
+                    qq = fmax(1.0 / qmax, fmin(1.0 / qmin, qq / gamma_c));
+                }
+                if (EEst <= 1.0) {
+                    cnt.n_acc++;
+                    qold = fmax(EEst, qoldinit);
+                    double dtnew = dt / qq;
+                    double ttmp = t + dt;
+                    if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
+                    const double h = ttmp - t;
+                    const double P_a = u[6], dP_a = k[0][6];
+                    t = ttmp;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) { u[i] = tmp[i]; k[0][i] = k[S - 1][i]; }
+                    if (u[6] < 0.0) {  // positivity callback (reference src/solve.jl:78-83,159-160)
+                        u[6] = 0.0;
+                        rhs_call(a.Tg, &rc, u, k[0], &cnt);
+                    }
+                    put_point(t, u, u[6], -k[0][6]);
+                    // streaming deposition over this step
+                    double R = sqrt(u[0] * u[0] + u[1] * u[1]), psi_b, pR, pZ;
+                    eval_psi(T, R, u[2], &psi_b, &pR, &pZ);
+                    double dpsi_b = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
+                    depo_step(dst, s_edges, n_psi, h, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, k[0][6], sink);
+                    psi_cur = psi_b; dpsi_cur = dpsi_b;
+                    dt = fmin(O.dtmax, dtnew);
+                } else {
+                    cnt.n_rej++;
+                    dt = dt / fmin(1.0 / qmin, q11 / gamma_c);
+                }
+            }
+        }
+        // ---- termination tests at the segment end (reference src/solve.jl:174-176) and retirement
+        if (act) {
+            bool done = TORJ_FATAL(rstat) || seg >= O.n_segments || psi_cur > O.psi_stop || u[6] < O.p_stop;
+            if (done) {
+                a.B.status[ray] = rstat;
+                a.B.n_points[ray] = npts;
+                if (!TORJ_FATAL(rstat)) {
+                    a.B.P_final[ray] = u[6];
+                    a.B.P_dep[ray] = pdep;
+                    tot_dep += wgt * pdep;
+                    tot_w += wgt;
+                    rays_ok++;
+                }
+                ray = -1;
+            }
+        }
+    }
+
+    // ---- block reduction: warp shuffles, shared-memory atomics, then global atomics
+    unsigned long long c6[6] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok};
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        tot_dep += __shfl_down_sync(FULL, tot_dep, off);
+        tot_w += __shfl_down_sync(FULL, tot_w, off);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) c6[q] += __shfl_down_sync(FULL, c6[q], off);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_tot[0], tot_dep);
+        atomicAdd(&s_tot[1], tot_w);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) atomicAdd(&s_cnt[q], c6[q]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_psi; j += blockDim.x)
+        if (s_bins[j] != 0.0) atomicAdd(&a.bins[j], s_bins[j]);
+    if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
+    if (threadIdx.x < 6) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
+__global__ void k_finalize(const double* bins, const double* dV, int n_psi, double* profile) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_psi - 1) profile[j] = bins[j] / dV[j];
+    else if (j == n_psi - 1) profile[j] = 0.0;
+    else if (j <= n_psi + 1) profile[j] = bins[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes
+// ------------------------------------------------------------------------------------------------
+// out[11][n]: psi, ne, Te, Bx, By, Bz, X, Y, N_par, Lambda, alpha
+__global__ void k_probe(DevTables T, long long n, const double* x, const double* N, double f, int mode, double te_min,
+                        int max_harmonic, double* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic);
+    double u[7] = {x[i], x[n + i], x[2 * n + i], N[i], N[n + i], N[2 * n + i], 1.0}, du[7];
+    Counters c = {0, 0, 0, 0, 0};
+    PointVals pv;
+    rhs<true>(T, rc, u, du, c, &pv);
+    double Babs = pv.Y / rc.cY;
+    out[i] = psi_at(T, u);
+    out[n + i] = pv.X / rc.cX;
+    out[2 * n + i] = pv.Te;
+    out[3 * n + i] = pv.b[0] * Babs; out[4 * n + i] = pv.b[1] * Babs; out[5 * n + i] = pv.b[2] * Babs;
+    out[6 * n + i] = pv.X; out[7 * n + i] = pv.Y; out[8 * n + i] = pv.N_par; out[9 * n + i] = pv.Lambda;
+    out[10 * n + i] = -du[6];
+}
+
+__global__ void k_rhs(DevTables T, long long n, const double* u, double f, int mode, double te_min, int max_harmonic,
+                      double* du) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic);
+    double uu[7], dd[7];
+    for (int q = 0; q < 7; ++q) uu[q] = u[(size_t)q * n + i];
+    Counters c = {0, 0, 0, 0, 0};
+    rhs<true>(T, rc, uu, dd, c);
+    for (int q = 0; q < 7; ++q) du[(size_t)q * n + i] = dd[q];
+}
+
+// FP64 peak: 8 independent DFMA chains per thread, register resident
+__global__ void k_dfma(int iters, double* out) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.6789) out[0] = s;
+}
+
+}  // namespace torj

@@ -1,0 +1,91 @@
+"""make_ray / make_beam — mirrors of reference src/solve.jl:135-181 and :209-242, calling libtorj_cuda.so."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_dp, c_ip
+from .launch import launch_peripheral_rays
+from .plasma import Plasma
+from .synthetic import pol_tor_angles_2_vector
+
+STATUS_TEXT = {
+    1: "cut-off at the vacuum/plasma boundary (reference src/solve.jl:55-59)",
+    2: "ray initialisation failed (assertions at reference src/solve.jl:32,138,141)",
+    3: "ray left the grid", 4: "step limit reached", 5: "NaN in the ray state",
+    6: "trajectory buffer too small",
+}
+
+
+def _p(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, mode, s_max, psi_dP_dV, *,
+                 options=None, ctx=None, trajectories=None, traj_max_pts=None):
+    """One torj_trace call on host buffers. trajectories: None or (first, count)."""
+    ctx = ctx or _lib.context()
+    L = _lib.lib()
+    pos = np.ascontiguousarray(np.asarray(ray_positions, dtype=np.float64).T)
+    dr = np.ascontiguousarray(np.asarray(ray_directions, dtype=np.float64).T)
+    n = pos.shape[1]
+    wt = np.ascontiguousarray(ray_weights, dtype=np.float64)
+    per_ray = int(np.ndim(f) > 0)
+    fr = np.ascontiguousarray(np.atleast_1d(f), dtype=np.float64)
+    md = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mode), fr.shape), dtype=np.int32)
+    psi = np.ascontiguousarray(psi_dP_dV, dtype=np.float64)
+    opt = options or _lib.default_options()
+    prof = np.zeros(len(psi)); dep = C.c_double()
+    Pf = np.zeros(n); Pd = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
+    cnt = _lib.TorjCounters()
+    t_first, t_count = trajectories if trajectories else (0, 0)
+    if t_count and traj_max_pts is None:
+        traj_max_pts = 2 + int(opt.n_segments * (np.ceil(s_max / opt.n_segments / opt.dtmax) + 8))
+    tm = int(traj_max_pts or 0)
+    ts = np.zeros((t_count, tm)); txyz = np.zeros((t_count, 3, tm)); tP = np.zeros((t_count, tm))
+    tdP = np.zeros((t_count, tm)); tprof = np.zeros((t_count, len(psi)))
+    _lib.check(L.torj_trace(ctx, plasma.handle(ctx), C.byref(opt), n, _p(pos), _p(dr), _p(wt), _p(fr),
+                            md.ctypes.data_as(c_ip), per_ray, float(s_max), len(psi), _p(psi), _p(prof), C.byref(dep),
+                            _p(Pf), _p(Pd), npts.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip), t_first, t_count, tm,
+                            _p(ts), _p(txyz), _p(tP), _p(tdP), _p(tprof), C.byref(cnt)))
+    return dict(dP_dV=prof, deposited_power=dep.value, P_final=Pf, P_deposited_ray=Pd, n_points=npts, status=st,
+                counters=cnt.as_dict(), traj_s=ts, traj_xyz=txyz, traj_P=tP, traj_dP_ds=tdP, traj_dP_dV_ray=tprof)
+
+
+def make_ray(plasma: Plasma, x0, N_vacuum, f, mode, s_max, psi_dP_dV, *, options=None, ctx=None):
+    """make_ray(plasma, x0, N_vacuum, f, mode, s_max, psi_dP_dV) -> (s, u, P_beam, dP_dV_ray, deposited_power)
+    — reference src/solve.jl:135-136,180.  u is the list of positions (first two: launch point, plasma entry)."""
+    r = trace_bundle(plasma, np.asarray(x0, dtype=np.float64)[None, :], np.asarray(N_vacuum, dtype=np.float64)[None, :],
+                     [1.0], float(f), int(mode), s_max, psi_dP_dV, options=options, ctx=ctx, trajectories=(0, 1))
+    st = int(r["status"][0])
+    if st not in (0,):
+        # the reference raises AssertionError / MethodError at src/solve.jl:32,138,141
+        raise AssertionError(STATUS_TEXT.get(st, f"ray status {st}"))
+    n = int(r["n_points"][0])
+    s = r["traj_s"][0, :n].copy()
+    u = [r["traj_xyz"][0, :, i].copy() for i in range(n)]
+    return s, u, r["traj_P"][0, :n].copy(), r["traj_dP_dV_ray"][0].copy(), float(r["P_deposited_ray"][0])
+
+
+def make_beam(plasma: Plasma, r, phi, z, steering_angle_tor, steering_angle_pol, spot_size, inverse_curvature_radius,
+              f, mode, s_max, psi_dP_dV, *, options=None, ctx=None, **kwargs):
+    """make_beam(...) -> (arc_lengths, trajectories, ray_powers, dP_dV, deposited_power, ray_weights)
+    — reference src/solve.jl:209-210,241; kwargs go to launch_peripheral_rays (src/solve.jl:216-217)."""
+    N0 = pol_tor_angles_2_vector(steering_angle_pol, steering_angle_tor)  # src/solve.jl:211
+    x0 = np.array([r * np.cos(phi), r * np.sin(phi), z])                  # src/solve.jl:212-215
+    pos, dirs, wts = launch_peripheral_rays(x0, N0, spot_size, inverse_curvature_radius, f, **kwargs)
+    n = len(wts)
+    res = trace_bundle(plasma, pos, dirs, wts, float(f), int(mode), s_max, psi_dP_dV, options=options, ctx=ctx,
+                       trajectories=(0, n))
+    bad = np.nonzero(~np.isin(res["status"], (0,)))[0]
+    if len(bad):
+        raise AssertionError(f"ray {int(bad[0])}: " + STATUS_TEXT.get(int(res['status'][bad[0]]), "failed"))
+    arc, traj, powers = [], [], []
+    for i in range(n):
+        m = int(res["n_points"][i])
+        arc.append(res["traj_s"][i, :m].copy())
+        traj.append([res["traj_xyz"][i, :, k].copy() for k in range(m)])
+        powers.append(res["traj_P"][i, :m].copy())
+    return arc, traj, powers, res["dP_dV"], res["deposited_power"], wts
