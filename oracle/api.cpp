@@ -190,11 +190,11 @@ int oracle_trace_bundle(void* h, const double* gl_t, const double* gl_w, int n_g
                         const double* pos, const double* dir, const double* weight, const double* freq,
                         const int32_t* mode, int per_ray_fm, double s_max, const double* psi_grid, int npsi,
                         int depo_kind, int n_threads, double* dP_dV, double* deposited_power, double* P_final,
-                        int32_t* n_points, int32_t* status, double* counters) {
+                        int32_t* n_points, int32_t* status, double* counters, double* dP_dV_streaming /* optional */) {
     Plasma* p = (Plasma*)h;
     AbsQuad q; q.t.assign(gl_t, gl_t + n_gl); q.w.assign(gl_w, gl_w + n_gl);
     Options opt = to_opts(o);
-    std::vector<double> prof(npsi, 0.0);
+    std::vector<double> prof(npsi, 0.0), prof2(npsi, 0.0);
     double dep = 0.0;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
 #ifdef _OPENMP
@@ -202,7 +202,7 @@ int oracle_trace_bundle(void* h, const double* gl_t, const double* gl_w, int n_g
 #endif
 #pragma omp parallel
     {
-        std::vector<double> lprof(npsi, 0.0), rayprof(npsi);
+        std::vector<double> lprof(npsi, 0.0), lprof2(npsi, 0.0), rayprof(npsi);
         double ldep = 0.0, l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0;
 #pragma omp for schedule(dynamic, 1)
         for (int64_t i = 0; i < n_rays; ++i) {
@@ -226,16 +226,22 @@ int oracle_trace_bundle(void* h, const double* gl_t, const double* gl_w, int n_g
                                              psi_grid, npsi, rayprof.data(), nullptr);
                 for (int j = 0; j < npsi; ++j) lprof[j] += rayprof[j] * weight[i];  // src/solve.jl:238
                 ldep += P * weight[i];                                              // src/solve.jl:239
+                if (dP_dV_streaming) {
+                    deposition_streaming(*p, r.s.data(), r.psi.data(), r.dpsi_ds.data(), r.P.data(), r.aP.data(), n,
+                                         psi_grid, npsi, rayprof.data(), nullptr);
+                    for (int j = 0; j < npsi; ++j) lprof2[j] += rayprof[j] * weight[i];
+                }
             }
             l0 += r.cnt.n_acc; l1 += r.cnt.n_rej; l2 += r.cnt.n_rhs; l3 += r.cnt.abs.n_alpha; l4 += r.cnt.abs.n_harm;
         }
 #pragma omp critical
         {
-            for (int j = 0; j < npsi; ++j) prof[j] += lprof[j];
+            for (int j = 0; j < npsi; ++j) { prof[j] += lprof[j]; prof2[j] += lprof2[j]; }
             dep += ldep; c0 += l0; c1 += l1; c2 += l2; c3 += l3; c4 += l4;
         }
     }
     for (int j = 0; j < npsi; ++j) dP_dV[j] = prof[j];
+    if (dP_dV_streaming) for (int j = 0; j < npsi; ++j) dP_dV_streaming[j] = prof2[j];
     *deposited_power = dep;
     if (counters) { counters[0] = c0; counters[1] = c1; counters[2] = c2; counters[3] = c3; counters[4] = c4; }
     return 0;
@@ -261,6 +267,13 @@ int oracle_fp_roots(void* s, double level, int maxn, double* out) {
     ((InterpSpline*)s)->roots(level, maxn, r);
     for (size_t i = 0; i < r.size(); ++i) out[i] = r[i];
     return (int)r.size();
+}
+
+// tableau of scheme (0 Tsit5, 1 OwrenZen3): a[7][7] row-major, btilde[7]; returns the number of stages
+int oracle_tableau(int scheme, double* a, double* bt) {
+    const Tableau& t = scheme == 1 ? tableau_owrenzen3() : tableau_tsit5();
+    for (int i = 0; i < 7; ++i) { for (int j = 0; j < 7; ++j) a[i * 7 + j] = t.a[i][j]; bt[i] = t.btilde[i]; }
+    return t.stages;
 }
 
 int oracle_max_threads() {

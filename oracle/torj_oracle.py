@@ -72,7 +72,7 @@ def lib():
         L.oracle_ray_free.argtypes = [C.c_void_p]
         L.oracle_trace_bundle.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int, C.POINTER(OracleOptions), C.c_int64, c_dp, c_dp,
                                           c_dp, c_dp, c_ip, C.c_int, C.c_double, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
-                                          c_dp, c_ip, c_ip, c_dp]
+                                          c_dp, c_ip, c_ip, c_dp, c_dp]
         L.oracle_fp_fit.restype = C.c_void_p
         L.oracle_fp_fit.argtypes = [c_dp, c_dp, C.c_int]
         L.oracle_fp_free.argtypes = [C.c_void_p]
@@ -82,6 +82,7 @@ def lib():
         L.oracle_fp_integral.restype = C.c_double
         L.oracle_fp_integral.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.oracle_fp_roots.argtypes = [C.c_void_p, C.c_double, C.c_int, c_dp]
+        L.oracle_tableau.argtypes = [C.c_int, c_dp, c_dp]
         _LIB = L
     return _LIB
 
@@ -188,8 +189,9 @@ class OraclePlasma:
             L.oracle_ray_free(rh)
 
     def trace_bundle(self, pos, dir, weight, freq, mode, s_max, psi_grid, gl, opts=None, deposition="faithful",
-                     n_threads=0):
-        """pos/dir: [N,3] arrays (as launch_peripheral_rays returns). freq/mode scalar or per-ray."""
+                     n_threads=0, also_streaming=False):
+        """pos/dir: [N,3] arrays (as launch_peripheral_rays returns). freq/mode scalar or per-ray.
+        also_streaming: additionally return the streaming-algorithm profile (key dP_dV_streaming) from the same rays."""
         L = lib()
         opts = opts or OracleOptions.default()
         pos = np.asarray(pos, dtype=np.float64); dir = np.asarray(dir, dtype=np.float64)
@@ -201,17 +203,29 @@ class OraclePlasma:
         t, pt = _d(gl[0]); w, pgw = _d(gl[1]); g, pg = _d(psi_grid)
         prof = np.zeros(len(g)); dep = C.c_double()
         Pf = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32); cnt = np.zeros(5)
+        prof2 = np.zeros(len(g)) if also_streaming else None
         L.oracle_trace_bundle(self.h, pt, pgw, len(t), C.byref(opts), n, pp, pd, pw, pf, md.ctypes.data_as(c_ip), per_ray,
                               s_max, pg, len(g), 0 if deposition == "faithful" else 1, n_threads, prof.ctypes.data_as(c_dp),
                               C.byref(dep), Pf.ctypes.data_as(c_dp), npts.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip),
-                              cnt.ctypes.data_as(c_dp))
-        return dict(dP_dV=prof, deposited_power=dep.value, P_final=Pf, n_points=npts, status=st,
+                              cnt.ctypes.data_as(c_dp), prof2.ctypes.data_as(c_dp) if also_streaming else None)
+        return dict(dP_dV_streaming=prof2, dP_dV=prof, deposited_power=dep.value, P_final=Pf, n_points=npts, status=st,
                     counters=dict(n_acc=cnt[0], n_rej=cnt[1], n_rhs=cnt[2], n_alpha=cnt[3], n_harm=cnt[4]))
 
 
 def abs_albajar(omega, X, Y, N_abs, N_par, Te, mode, gl, te_min=20.0, max_harmonic=3):
     t, pt = _d(gl[0]); w, pw = _d(gl[1])
     return lib().oracle_abs_albajar(pt, pw, len(t), omega, X, Y, N_abs, N_par, Te, mode, te_min, max_harmonic)
+
+
+def tableau(scheme):
+    """(a[S,S], btilde[S]) of the oracle's RK scheme (0 Tsit5, 1 OwrenZen3); last row of a is b (FSAL)."""
+    a = np.zeros(49); bt = np.zeros(7)
+    S = lib().oracle_tableau(scheme, a.ctypes.data_as(c_dp), bt.ctypes.data_as(c_dp))
+    return a.reshape(7, 7)[:S, :S].copy(), bt[:S].copy()
+
+
+def max_threads():
+    return lib().oracle_max_threads()
 
 
 def besselj(n, x):

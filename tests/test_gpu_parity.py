@@ -1,0 +1,316 @@
+"""Parity of the CUDA path (through the C ABI of libtorj_cuda.so) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star, SURVEY.md §8(d) "Parity gates"), all FP64:
+  trajectories            <= 1e-9 m at equal step sequences (same number of saved points required)
+  final absorbed fraction <= 1e-6 relative
+  deposition profile      ||d||_2/||ref||_2 <= 1e-4 against the reference's spline-root algorithm ("faithful"),
+                          <= 1e-9 against the oracle's restatement of the streaming algorithm (like for like)
+"""
+import numpy as np
+import pytest
+
+import torj_jl_b200 as tj
+from oracle import torj_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PSI = np.linspace(0.0, 1.0, 1000)  # reference test/tests/setup.jl:77
+TRAJ_TOL = 1e-9
+FRAC_TOL = 1e-6
+L2_FAITHFUL = 1e-4
+L2_LIKE = 1e-9
+
+
+def l2rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def gpu_full(arrays_full):
+    tj.abs_Al_init(24)  # reference test/tests/setup.jl:80
+    return tj.Plasma(*arrays_full.values())
+
+
+@pytest.fixture(scope="module")
+def gpu_small(arrays_small):
+    tj.abs_Al_init(24)
+    return tj.Plasma(*arrays_small.values())
+
+
+def _ray_points(res, i=0):
+    n = int(res["n_points"][i])
+    return n, res["traj_s"][i, :n], res["traj_xyz"][i, :, :n], res["traj_P"][i, :n], res["traj_dP_ds"][i, :n]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fields, dispersion, absorption, RHS  (reference test/tests/test_trajectory.jl, test_absorption.jl)
+# ------------------------------------------------------------------------------------------------------------------
+def test_fields_and_dispersion_along_ray(gpu_full, oracle_full, gl24, launcher):
+    ro = oracle_full.make_ray(launcher["x0"], launcher["N0"], launcher["f"], 1, 0.4, PSI, gl24)
+    idx = np.linspace(1, len(ro["s"]) - 1, 200).astype(int)
+    X = np.stack([ro["x"][idx], ro["y"][idx], ro["z"][idx]], 1)
+    rng = np.random.default_rng(1)
+    N = rng.normal(size=X.shape) * 0.5
+    pr = gpu_full.probe(X, N, launcher["f"], 1)
+    om = 2 * np.pi * launcher["f"]
+    for i in range(0, len(idx), 7):
+        e = oracle_full.eval_plasma(X[i], N[i], om, 1)
+        assert abs(pr["X"][i] - e["X"]) <= 1e-13 * e["X"]
+        assert abs(pr["Y"][i] - e["Y"]) < 1e-14
+        assert abs(pr["N_par"][i] - e["N_par"]) < 1e-14
+        assert abs(pr["Te"][i] - e["Te"]) <= 1e-12 * e["Te"]
+        assert abs(pr["Lambda"][i] - e["Lambda"]) < 1e-13
+        assert abs(pr["psi"][i] - ro["psi"][idx[i]]) < 1e-14
+        Babs = e["Y"] * 9.1093837015e-31 * om / 1.602176634e-19
+        assert np.abs(pr["B"][i] - e["b"] * Babs).max() < 1e-6          # test_trajectory.jl:10 asks 1e-6 T
+
+
+def test_fields_outside_the_grid_use_line_extrapolation(gpu_small, oracle_small, arrays_small):
+    R = arrays_small["R_coords"]; Z = arrays_small["Z_coords"]
+    pts = np.array([[R[-1] + 0.3, 0.0, 0.2], [0.0, R[0] - 0.1, Z[0] - 0.2], [1.2, 0.9, Z[-1] + 0.05], [R[-1], 0.0, Z[-1]]])
+    N = np.tile([0.3, 0.2, -0.1], (len(pts), 1))
+    pr = gpu_small.probe(pts, N, 95e9, 1)
+    for i, p in enumerate(pts):
+        v, _, _ = oracle_small.spline("psi", [np.hypot(p[0], p[1])], [p[2]])
+        assert abs(pr["psi"][i] - v[0]) < 1e-12 * max(1.0, abs(v[0]))
+        e = oracle_small.eval_plasma(p, N[i], 2 * np.pi * 95e9, 1)
+        assert abs(pr["Y"][i] - e["Y"]) < 1e-13 and abs(pr["N_par"][i] - e["N_par"]) < 1e-13
+
+
+def test_rhs_matches_dual_number_oracle(gpu_full, oracle_full, gl24, launcher):
+    """Hand-derived gradients (kernel) vs ForwardDiff-style duals (oracle), X and O mode, with toroidal angle."""
+    for mode, tor in ((1, 0.0), (-1, 0.0), (1, 0.25)):
+        N0 = tj.pol_tor_angles_2_vector(np.deg2rad(25.0), tor)
+        st, init = oracle_full.ray_init(launcher["x0"], N0, launcher["f"], mode)
+        assert st == 0
+        u = np.concatenate([init[:6], [0.7]])
+        U = []
+        for _ in range(45):
+            U.append(u.copy())
+            u = u + 0.008 * oracle_full.rhs(u, launcher["f"], mode, gl24)
+        U = np.array(U)
+        dg = gpu_full.rhs(U, launcher["f"], mode)
+        do = np.array([oracle_full.rhs(v, launcher["f"], mode, gl24) for v in U])
+        assert np.abs(dg[:, :3] - do[:, :3]).max() < 1e-13
+        assert np.abs(dg[:, 3:6] - do[:, 3:6]).max() < 1e-11
+        scale = np.maximum(np.abs(do[:, 6]), 1e-300)
+        assert (np.abs(dg[:, 6] - do[:, 6]) / scale)[np.abs(do[:, 6]) > 1e-250].max() < 1e-11
+
+
+def test_absorption_coefficient_scan(gpu_full, oracle_full, gl24):
+    """alpha over the second/third-harmonic layer incl. Bessel-series range switches; Te gate (src/absorption.jl:194)."""
+    R = np.linspace(1.45, 2.28, 120)
+    X = np.stack([R, np.zeros_like(R), 0.05 * np.ones_like(R)], 1)
+    for ang in (0.0, 0.3, 0.6):
+        N = np.tile([-0.9 * np.cos(ang), 0.9 * np.sin(ang), -0.1], (len(R), 1))
+        for mode in (1, -1):
+            a = gpu_full.probe(X, N, 95e9, mode)["alpha"]
+            ref = -np.array([oracle_full.rhs(np.concatenate([X[i], N[i], [1.0]]), 95e9, mode, gl24)[6] for i in range(len(R))])
+            big = np.abs(ref) > 1e-200
+            assert np.abs(a[big] - ref[big]).max() <= 1e-10 * np.abs(ref[big]).max()
+            assert (np.abs(a[big] - ref[big]) / np.abs(ref[big])).max() < 1e-9
+    opt = tj.default_options(te_min=1e9)
+    assert np.all(gpu_full.probe(X, N, 95e9, 1, options=opt)["alpha"] == 0.0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ray initialisation
+# ------------------------------------------------------------------------------------------------------------------
+def test_ray_init_matches_oracle(gpu_full, oracle_full, launcher):
+    N0 = tj.pol_tor_angles_2_vector(np.deg2rad(28.0), 0.15)
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], N0, launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    res = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1e-3, PSI, options=tj.default_options(n_segments=1),
+                          trajectories=(0, len(w)), traj_max_pts=16)
+    assert (res["status"] == 0).all()
+    for i in range(0, len(w), 5):
+        st, init = oracle_full.ray_init(pos[i], dirs[i], launcher["f"], 1)
+        assert st == 0
+        assert np.abs(res["traj_xyz"][i, :, 1] - init[:3]).max() < 1e-12
+        assert abs(res["traj_s"][i, 1] - init[6]) < 1e-12
+
+
+def test_init_failure_statuses_do_not_abort_the_batch(gpu_small, arrays_small, launcher):
+    pos = np.array([launcher["x0"], launcher["x0"], launcher["x0"] - 0.9 * launcher["N0"]])
+    dirs = np.array([launcher["N0"], -launcher["N0"], launcher["N0"]])
+    res = tj.trace_bundle(gpu_small, pos, dirs, [0.5, 0.25, 0.25], launcher["f"], 1, 0.3, np.linspace(0, 1, 64))
+    assert list(res["status"]) == [0, 2, 0]                 # second ray points away: no bracket (src/solve.jl:29)
+    assert res["counters"]["n_rays_ok"] == 2 and res["P_final"][1] == 0.0 and res["n_points"][1] == 0
+    assert abs(res["P_final"][0] - res["P_final"][2]) < 1e-9   # off-grid launcher enters through the box (src/solve.jl:22-25)
+    dense = dict(arrays_small); dense["ne_prof"] = np.full_like(dense["ne_prof"], 1e20)
+    r2 = tj.trace_bundle(tj.Plasma(*dense.values()), pos[:1], dirs[:1], [1.0], 60e9, 1, 0.3, np.linspace(0, 1, 64))
+    assert list(r2["status"]) == [1]                        # cut-off at entry (src/solve.jl:55-59)
+    with pytest.raises(AssertionError, match="cut-off"):
+        tj.make_ray(tj.Plasma(*dense.values()), pos[0], dirs[0], 60e9, 1, 0.3, np.linspace(0, 1, 64))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 1: single EC ray (stand-in for reference test/tests/test_make_ray.jl)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,scheme", [(1, 0), (-1, 0), (1, 1)])
+def test_config1_single_ray_trajectory(gpu_full, oracle_full, gl24, launcher, mode, scheme):
+    opt = tj.default_options(scheme=scheme)
+    s, u, P, prof, dep = tj.make_ray(gpu_full, launcher["x0"], launcher["N0"], launcher["f"], mode, 0.4, PSI, options=opt)
+    ro = oracle_full.make_ray(launcher["x0"], launcher["N0"], launcher["f"], mode, 0.4, PSI, gl24,
+                              opts=O.OracleOptions.default(scheme=scheme))
+    assert ro["status"] == 0 and len(s) == len(ro["s"])
+    xyz = np.array(u)
+    assert np.abs(s - ro["s"]).max() < 1e-12
+    assert max(np.abs(xyz[:, 0] - ro["x"]).max(), np.abs(xyz[:, 1] - ro["y"]).max(), np.abs(xyz[:, 2] - ro["z"]).max()) < TRAJ_TOL
+    assert np.abs(P - ro["P"]).max() < 1e-9
+    if ro["deposited_power"] > 1e-8:
+        assert abs(dep - ro["deposited_power"]) <= FRAC_TOL * ro["deposited_power"]
+        assert l2rel(prof, ro["dP_dV"]) < L2_FAITHFUL
+        rs = oracle_full.make_ray(launcher["x0"], launcher["N0"], launcher["f"], mode, 0.4, PSI, gl24,
+                                  opts=O.OracleOptions.default(scheme=scheme), deposition="streaming")
+        assert l2rel(prof, rs["dP_dV"]) < L2_LIKE
+
+
+def test_make_ray_return_shapes(gpu_small, launcher):
+    """reference src/solve.jl:180: (s, u, P_beam, dP_dV_ray, deposited_power)."""
+    psi = np.linspace(0, 1, 50)
+    s, u, P, prof, dep = tj.make_ray(gpu_small, launcher["x0"], launcher["N0"], launcher["f"], 1, 0.1, psi)
+    assert s.ndim == 1 and len(u) == len(s) == len(P) and u[0].shape == (3,) and prof.shape == (50,) and isinstance(dep, float)
+    assert s[0] == 0.0 and np.allclose(u[0], launcher["x0"]) and P[0] == P[1] == 1.0 and prof[-1] == 0.0
+    assert len(s) == 2 + 100 * 10                                   # 100 segments of 1 mm at dtmax = 0.1 mm
+    assert abs(s[-1] - s[1] - 0.1) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 2: 1 025-ray beam, absorbed fraction + deposition profile
+# ------------------------------------------------------------------------------------------------------------------
+def test_config2_beam_1025_rays(gpu_full, oracle_full, gl24, launcher):
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=7, min_azimuthal_points=20)
+    assert len(w) == 1025
+    res = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI)
+    ref = oracle_full.trace_bundle(pos, dirs, w, launcher["f"], 1, 1.0, PSI, gl24, deposition="faithful", also_streaming=True)
+    assert (res["status"] == 0).all() and (ref["status"] == 0).all()
+    assert np.array_equal(res["n_points"], ref["n_points"])
+    assert res["counters"]["n_acc"] == int(ref["counters"]["n_acc"]) and res["counters"]["n_rej"] == int(ref["counters"]["n_rej"])
+    assert np.abs(res["P_final"] - ref["P_final"]).max() < 1e-12
+    assert abs(res["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(res["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
+    assert l2rel(res["dP_dV"], ref["dP_dV_streaming"]) < L2_LIKE
+    # identities of reference test/tests/test_make_beam.jl:14-31
+    absorbed = 1.0 - float(np.sum(w * res["P_final"]))
+    assert abs(res["deposited_power"] - absorbed) < 1e-3
+    dpsi = PSI[1] - PSI[0]
+    dVdpsi = (gpu_full.volume(PSI + 1e-6) - gpu_full.volume(PSI - 1e-6)) / 2e-6
+    assert abs(float(np.sum(dVdpsi * res["dP_dV"] * dpsi)) - res["deposited_power"]) < 1e-3
+
+
+def test_make_beam_default_bundle(gpu_full, oracle_full, gl24, launcher):
+    """make_beam(...) of reference src/solve.jl:209-242 with the default 46-ray bundle and kwargs pass-through."""
+    arc, traj, powers, prof, dep, w = tj.make_beam(gpu_full, 2.5, 0.0, 0.4, 0.0, np.deg2rad(30.0), launcher["spot"],
+                                                    launcher["inv_Rc"], launcher["f"], 1, 1.0, PSI)
+    assert len(arc) == len(traj) == len(powers) == len(w) == 46 and prof.shape == PSI.shape
+    pos, dirs, w2 = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    ref = oracle_full.trace_bundle(pos, dirs, w2, launcher["f"], 1, 1.0, PSI, gl24)
+    assert abs(dep - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(prof, ref["dP_dV"]) < L2_FAITHFUL
+    assert all(abs(powers[i][-1] - ref["P_final"][i]) < 1e-12 for i in range(46))
+    out = tj.make_beam(gpu_full, 2.5, 0.0, 0.4, 0.0, np.deg2rad(30.0), launcher["spot"], launcher["inv_Rc"], launcher["f"], 1,
+                       0.2, PSI, N_rings=2, min_azimuthal_points=3)
+    assert len(out[5]) == 3 + round(3 * np.polynomial.hermite.hermgauss(6)[0][4] / np.polynomial.hermite.hermgauss(6)[0][3])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weak absorption / exits / odd grids / per-ray frequency
+# ------------------------------------------------------------------------------------------------------------------
+def test_low_density_o_mode_rays_leave_the_plasma(arrays_small, gl24, launcher):
+    arr = dict(arrays_small); arr["ne_prof"] = arr["ne_prof"] * 0.3; arr["Te_prof"] = arr["Te_prof"] * 0.25
+    pl = tj.Plasma(*arr.values()); opl = O.OraclePlasma(*arr.values())
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], 140e9,
+                                             N_rings=2, min_azimuthal_points=3)
+    psi = np.concatenate([np.linspace(0, 0.5, 40) ** 2 * 2, np.linspace(0.51, 1.0, 70)])   # non-uniform levels
+    res = tj.trace_bundle(pl, pos, dirs, w, 140e9, -1, 3.0, psi, trajectories=(0, 2))
+    ref = opl.trace_bundle(pos, dirs, w, 140e9, -1, 3.0, psi, gl24)
+    assert (res["status"] == 0).all() and np.array_equal(res["n_points"], ref["n_points"])
+    assert res["n_points"].max() < 2 + 100 * 300                   # stopped by psi > 1 (src/solve.jl:174), not by s_max
+    assert np.abs(res["P_final"] - ref["P_final"]).max() < 1e-10
+    assert 0.0 < ref["deposited_power"] < 0.999
+    assert abs(res["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(res["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
+    ro = opl.make_ray(pos[1], dirs[1], 140e9, -1, 3.0, psi, gl24)
+    n, s, xyz, P, dP = _ray_points(res, 1)
+    assert n == len(ro["s"]) and np.abs(xyz[0] - ro["x"]).max() < TRAJ_TOL and np.abs(xyz[2] - ro["z"]).max() < TRAJ_TOL
+    assert np.abs(dP - ro["dP_ds"]).max() <= 1e-9 * max(1.0, np.abs(ro["dP_ds"]).max())
+
+
+def test_per_ray_frequency_and_mode(gpu_small, oracle_small, gl24, launcher):
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], 95e9,
+                                             N_rings=2, min_azimuthal_points=3)
+    n = len(w)
+    f = np.where(np.arange(n) % 2 == 0, 95e9, 110e9)
+    mode = np.where(np.arange(n) % 3 == 0, -1, 1)
+    psi = np.linspace(0, 1, 120)
+    res = tj.trace_bundle(gpu_small, pos, dirs, w, f, mode, 0.5, psi)
+    ref = oracle_small.trace_bundle(pos, dirs, w, f, mode, 0.5, psi, gl24)
+    assert np.array_equal(res["n_points"], ref["n_points"]) and np.abs(res["P_final"] - ref["P_final"]).max() < 1e-11
+    assert l2rel(res["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
+
+
+def test_smallest_inputs(gpu_small, launcher):
+    r = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 1.0]))
+    assert r["status"][0] == 0 and r["dP_dV"].shape == (2,) and r["dP_dV"][1] == 0.0
+    with pytest.raises(tj.TorjError, match="strictly increasing"):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 0.5, 0.5]))
+    with pytest.raises(tj.TorjError):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.5]))
+    with pytest.raises(tj.TorjError, match="scheme"):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, PSI,
+                        options=tj.default_options(scheme=7))
+
+
+def test_trajectory_window_truncation_keeps_physics(gpu_small, launcher):
+    psi = np.linspace(0, 1, 100)
+    a = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.3, psi, trajectories=(0, 1))
+    b = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.3, psi, trajectories=(0, 1),
+                        traj_max_pts=100)
+    assert a["status"][0] == 0 and b["status"][0] == 6
+    assert a["n_points"][0] == b["n_points"][0] and a["P_final"][0] == b["P_final"][0]
+    assert np.array_equal(a["traj_s"][0, :100], b["traj_s"][0, :100])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 3 size (65 543 rays): size-independent properties
+# ------------------------------------------------------------------------------------------------------------------
+def test_config3_full_size_properties(gpu_full, oracle_full, gl24, launcher):
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=66, min_azimuthal_points=14)
+    n = len(w)
+    assert n == 65543
+    res = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI)
+    assert (res["status"] == 0).all() and res["counters"]["n_rays_ok"] == n
+    assert res["counters"]["n_acc"] == int(np.sum(res["n_points"] - 2))
+    # reference test/tests/test_make_beam.jl:14-31 identities
+    absorbed = 1.0 - float(np.sum(w * res["P_final"]))
+    assert abs(res["deposited_power"] - absorbed) < 1e-3
+    assert abs(float(np.sum(w * res["P_deposited_ray"])) - res["deposited_power"]) < 1e-12
+    dpsi = PSI[1] - PSI[0]
+    dVdpsi = (gpu_full.volume(PSI + 1e-6) - gpu_full.volume(PSI - 1e-6)) / 2e-6
+    assert abs(float(np.sum(dVdpsi * res["dP_dV"] * dpsi)) - res["deposited_power"]) < 1e-3
+    # linearity over shards: two halves (different refill order, different atomics order) add up to the whole
+    h = n // 2
+    a = tj.trace_bundle(gpu_full, pos[:h], dirs[:h], w[:h], launcher["f"], 1, 1.0, PSI)
+    b = tj.trace_bundle(gpu_full, pos[h:], dirs[h:], w[h:], launcher["f"], 1, 1.0, PSI)
+    assert np.array_equal(np.concatenate([a["P_final"], b["P_final"]]), res["P_final"])
+    assert np.abs(a["dP_dV"] + b["dP_dV"] - res["dP_dV"]).max() <= 1e-12 * res["dP_dV"].max()
+    # spot check of 24 rays spread over the bundle against the oracle
+    pick = np.linspace(0, n - 1, 24).astype(int)
+    ref = oracle_full.trace_bundle(pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, gl24, deposition="streaming")
+    assert np.array_equal(res["n_points"][pick], ref["n_points"])
+    assert np.abs(res["P_final"][pick] - ref["P_final"]).max() < 1e-12
+    sub = tj.trace_bundle(gpu_full, pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI)
+    assert l2rel(sub["dP_dV"], ref["dP_dV"]) < L2_LIKE
+
+
+def test_fp64_peak_probe_and_launch_counter():
+    import ctypes as C
+    from torj_jl_b200 import _lib
+    ctx = _lib.context()
+    n0 = tj.lib().torj_ctx_launch_count(ctx)
+    tf, ms = C.c_double(), C.c_double()
+    _lib.check(tj.lib().torj_fp64_peak(ctx, 4000, C.byref(tf), C.byref(ms)))
+    assert 20.0 < tf.value < 45.0                                  # nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2
+    assert tj.lib().torj_ctx_launch_count(ctx) == n0 + 2

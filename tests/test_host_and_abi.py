@@ -1,0 +1,130 @@
+"""Host logic of the reference-facing mirror and the C-ABI surface.  CPU only (no compute calls on the library)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+import torj_jl_b200 as tj
+from torj_jl_b200 import _lib
+from torj_jl_b200.distributed import shard_range
+from oracle import torj_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "torj_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(torj_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/torj_cuda.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert tj.lib().torj_abi_version() == 1
+
+
+def test_default_options_are_the_reference_constants():
+    o = tj.default_options()
+    assert (o.scheme, o.n_segments, o.max_harmonic) == (0, 100, 3)           # src/solve.jl:145, src/absorption.jl:199
+    assert (o.dtmax, o.abstol, o.reltol) == (1e-4, 1e-6, 1e-6)               # src/solve.jl:157
+    assert (o.psi_stop, o.p_stop, o.te_min) == (1.0, 1e-6, 20.0)             # src/solve.jl:174,176; src/absorption.jl:194
+    with pytest.raises(AttributeError):
+        tj.default_options(nonexistent=1)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the loud failure on a box without CUDA")
+def test_no_cpu_fallback():
+    with pytest.raises(tj.TorjError, match="no CUDA device"):
+        tj.abs_Al_init(24)
+
+
+def test_plasma_tables_match_oracle(arrays_small, oracle_small):
+    pl = tj.Plasma(*arrays_small.values())
+    for k in ("psi", "lnne", "lnTe", "BR", "BZ", "Bphi"):
+        ref = oracle_small.coefs(k)
+        assert pl.coefs[k].shape == ref.shape == (67, 67)
+        assert np.abs(pl.coefs[k] - ref).max() <= 1e-13 * np.abs(ref).max()
+    vc, x0, dx = oracle_small.volume_coefs()
+    assert np.abs(vc - pl.vol_coef).max() < 1e-13 and (x0, dx) == (pl.vol_psi0, pl.vol_dpsi)
+    assert pl.psi_prof_max == oracle_small.psi_prof_max == 1.0
+    psi = np.array([-0.1, 0.0, 0.37, 1.0, 1.2])
+    assert np.abs(pl.volume(psi) - oracle_small.volume(psi)).max() < 1e-13
+    with pytest.raises(ValueError):
+        bad = dict(arrays_small); bad["psi_norm_data"] = bad["psi_norm_data"][:, :-1]
+        tj.Plasma(*bad.values())
+
+
+def test_nonuniform_profile_grid_is_resampled(arrays_small):
+    """make_2d_prof_spline resamples the 1-D profile on a uniform psi range (reference src/plasma.jl:17-18)."""
+    arr = dict(arrays_small)
+    psi = np.linspace(0, 1, 101) ** 1.5
+    arr["psi_prof"] = psi
+    arr["ne_prof"] = 3e19 * (1 - psi) + 1e17
+    arr["Te_prof"] = 4e3 * (1 - psi) ** 2 + 50
+    pl = tj.Plasma(*arr.values())
+    opl = O.OraclePlasma(*arr.values())
+    for k in ("lnne", "lnTe"):
+        ref = opl.coefs(k)
+        assert np.abs(pl.coefs[k] - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_launch_matches_oracle_and_reference_counts(launcher):
+    for kw in (dict(), dict(N_rings=7, min_azimuthal_points=20), dict(N_rings=21, min_azimuthal_points=11, normalize_weight_sum=False)):
+        for tor in (0.0, 0.2):
+            N0 = tj.pol_tor_angles_2_vector(np.deg2rad(25.0), tor)
+            a = tj.launch_peripheral_rays(launcher["x0"], N0, launcher["spot"], launcher["inv_Rc"], launcher["f"], **kw)
+            b = O.launch_peripheral_rays(launcher["x0"], N0, launcher["spot"], launcher["inv_Rc"], launcher["f"], **kw)
+            assert a[0].shape == b[0].shape
+            for x, y in zip(a, b):
+                assert np.abs(x - y).max() < 1e-13
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    assert pos.shape == (46, 3) and abs(w.sum() - 1) < 1e-14           # default bundle: N_theta = 5, 15, 26
+    # convergent beam and paraxial beam branches (src/launch.jl:102-117)
+    pc = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], 0.03, -1 / 2.0, 95e9)
+    oc = O.launch_peripheral_rays(launcher["x0"], launcher["N0"], 0.03, -1 / 2.0, 95e9)
+    assert np.abs(pc[1] - oc[1]).max() < 1e-13
+    pp = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], 0.03, np.inf, 95e9)
+    assert np.allclose(pp[1], launcher["N0"] / np.linalg.norm(launcher["N0"]))
+    with pytest.raises(ValueError, match="N_rings = 1 < 2"):
+        tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], 0.03, 0.25, 95e9, N_rings=1)
+
+
+def test_weights_integrate_a_gaussian():
+    """reference test/tests/test_launch_weights.jl:27-50."""
+    p, d, w = tj.launch_peripheral_rays([0, 0, 0.0], [0, 0, 1.0], 0.0174, 1 / 3.99, 92.5e9, N_rings=21, min_azimuthal_points=11,
+                                        normalize_weight_sum=False)
+    assert len(w) == 5165 and abs(w.sum() - 1.0) / 1.0 < 0.01
+
+
+def test_pol_tor_vector():
+    v = tj.pol_tor_angles_2_vector(np.deg2rad(30.0), 0.0)
+    assert np.allclose(v, [-np.sqrt(3) / 2, 0.0, -0.5]) and abs(np.linalg.norm(v) - 1) < 1e-15
+
+
+def test_shard_range_partitions():
+    for n in (1, 46, 1025, 65543, 1049600):
+        for ws in (1, 2, 3, 4, 8):
+            parts = [shard_range(n, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_prefilter_helpers_match_scipy():
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=37)
+    c = np.empty(39)
+    _lib.check(tj.lib().torj_bspline_prefilter_1d(37, y.ctypes.data_as(_lib.c_dp), c.ctypes.data_as(_lib.c_dp)))
+    x = np.arange(37.0)
+    cs = CubicSpline(x, y, bc_type="natural")
+    xq = np.linspace(0, 36, 400)
+    from torj_jl_b200.plasma import _eval_1d_line
+    assert np.abs(_eval_1d_line(c, 0.0, 1.0, 37, xq) - cs(xq)).max() < 1e-13
+    for n in (2, 3, 4):
+        yy = rng.normal(size=n); cc = np.empty(n + 2)
+        _lib.check(tj.lib().torj_bspline_prefilter_1d(n, yy.ctypes.data_as(_lib.c_dp), cc.ctypes.data_as(_lib.c_dp)))
+        assert np.abs(_eval_1d_line(cc, 0.0, 1.0, n, np.arange(n * 1.0)) - yy).max() < 1e-14
