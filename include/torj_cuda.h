@@ -53,6 +53,10 @@ typedef struct torj_options {
     double te_min;                 /* 20 eV src/absorption.jl:194 */
     int32_t max_harmonic;          /* 3     src/absorption.jl:199 */
     int32_t max_steps_per_segment; /* safety cap, 100000 */
+    double alpha_floor;            /* 1e-14 m^-1: a harmonic integral (src/absorption.jl:170-189) is skipped when a rigorous
+                                      upper bound of its contribution to alpha is below this (|J_n|<=1, sum of weights 2,
+                                      max exponent on the resonance curve); optical-depth error <= 2*alpha_floor*path.
+                                      0 = evaluate every integral exactly as the reference does */
 } torj_options;
 
 typedef struct torj_counters {
@@ -62,6 +66,7 @@ typedef struct torj_counters {
     int64_t n_alpha; /* abs_Albajar_fast calls past the Te gate (src/absorption.jl:194) */
     int64_t n_harm;  /* harmonic integrals evaluated (src/absorption.jl:217) */
     int64_t n_rays_ok;
+    int64_t n_harm_pruned; /* harmonic integrals skipped by the alpha_floor bound */
 } torj_counters;
 
 typedef struct torj_grid {

@@ -19,7 +19,7 @@ using namespace torj_oracle;
 
 extern "C" {
 
-struct oracle_options {  // mirrors torj_options in include/torj_cuda.h field for field
+struct oracle_options {  // the reference's hard-coded solver constants (the oracle has no alpha_floor: it is exact)
     int32_t scheme;
     int32_t n_segments;
     double dtmax, abstol, reltol, psi_stop, p_stop, te_min;

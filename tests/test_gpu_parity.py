@@ -21,6 +21,11 @@ L2_FAITHFUL = 1e-4
 L2_LIKE = 1e-9
 
 
+def EXACT():
+    """alpha_floor = 0: every harmonic integral evaluated, as the reference does."""
+    return tj.default_options(alpha_floor=0.0)
+
+
 def l2rel(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
@@ -89,7 +94,7 @@ def test_rhs_matches_dual_number_oracle(gpu_full, oracle_full, gl24, launcher):
             U.append(u.copy())
             u = u + 0.008 * oracle_full.rhs(u, launcher["f"], mode, gl24)
         U = np.array(U)
-        dg = gpu_full.rhs(U, launcher["f"], mode)
+        dg = gpu_full.rhs(U, launcher["f"], mode, options=EXACT())
         do = np.array([oracle_full.rhs(v, launcher["f"], mode, gl24) for v in U])
         assert np.abs(dg[:, :3] - do[:, :3]).max() < 1e-13
         assert np.abs(dg[:, 3:6] - do[:, 3:6]).max() < 1e-11
@@ -104,7 +109,9 @@ def test_absorption_coefficient_scan(gpu_full, oracle_full, gl24):
     for ang in (0.0, 0.3, 0.6):
         N = np.tile([-0.9 * np.cos(ang), 0.9 * np.sin(ang), -0.1], (len(R), 1))
         for mode in (1, -1):
-            a = gpu_full.probe(X, N, 95e9, mode)["alpha"]
+            a = gpu_full.probe(X, N, 95e9, mode, options=EXACT())["alpha"]
+            pruned = gpu_full.probe(X, N, 95e9, mode)["alpha"]          # default alpha_floor = 1e-14 1/m
+            assert np.abs(pruned - a).max() <= 2e-14 and np.any(pruned != a) and np.any(pruned == 0.0)
             ref = -np.array([oracle_full.rhs(np.concatenate([X[i], N[i], [1.0]]), 95e9, mode, gl24)[6] for i in range(len(R))])
             big = np.abs(ref) > 1e-200
             assert np.abs(a[big] - ref[big]).max() <= 1e-10 * np.abs(ref[big]).max()
@@ -163,6 +170,19 @@ def test_config1_single_ray_trajectory(gpu_full, oracle_full, gl24, launcher, mo
         rs = oracle_full.make_ray(launcher["x0"], launcher["N0"], launcher["f"], mode, 0.4, PSI, gl24,
                                   opts=O.OracleOptions.default(scheme=scheme), deposition="streaming")
         assert l2rel(prof, rs["dP_dV"]) < L2_LIKE
+
+
+def test_alpha_floor_pruning_is_invisible_at_tolerance(gpu_full, launcher):
+    """Default alpha_floor (1e-14 1/m) against exact evaluation on the default 46-ray beam."""
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    a = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI)
+    b = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=EXACT())
+    assert a["counters"]["n_harm_pruned"] > 0 and b["counters"]["n_harm_pruned"] == 0
+    assert a["counters"]["n_harm"] + a["counters"]["n_harm_pruned"] == b["counters"]["n_harm"]
+    assert np.array_equal(a["n_points"], b["n_points"])
+    assert np.abs(a["P_final"] - b["P_final"]).max() < 1e-13
+    assert abs(a["deposited_power"] - b["deposited_power"]) < 1e-12
+    assert l2rel(a["dP_dV"], b["dP_dV"]) < 1e-12
 
 
 def test_make_ray_return_shapes(gpu_small, launcher):

@@ -30,6 +30,7 @@ def test_default_options_are_the_reference_constants():
     assert (o.scheme, o.n_segments, o.max_harmonic) == (0, 100, 3)           # src/solve.jl:145, src/absorption.jl:199
     assert (o.dtmax, o.abstol, o.reltol) == (1e-4, 1e-6, 1e-6)               # src/solve.jl:157
     assert (o.psi_stop, o.p_stop, o.te_min) == (1.0, 1e-6, 20.0)             # src/solve.jl:174,176; src/absorption.jl:194
+    assert o.alpha_floor == 1e-14
     with pytest.raises(AttributeError):
         tj.default_options(nonexistent=1)
 

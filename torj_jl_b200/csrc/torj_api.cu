@@ -90,6 +90,7 @@ void torj_options_default(torj_options* o) {
     o->te_min = 20.0;
     o->max_harmonic = 3;
     o->max_steps_per_segment = 100000;
+    o->alpha_floor = 1e-14;
 }
 
 static void fill_tableaux(Tableau t[2]) {
@@ -142,6 +143,10 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
         for (int k = 1; k < TORJ_BESS_K; ++k) bc[n][k] = -bc[n][k - 1] / ((double)k * (double)(n + k));
     }
     CK(cudaMemcpyToSymbol(c_bess, bc, sizeof bc));
+    double bd[5][TORJ_BESS_K];
+    for (int n = 0; n < 5; ++n)
+        for (int k = 0; k < TORJ_BESS_K; ++k) bd[n][k] = (double)(n + 2 * k) * bc[n][k];
+    CK(cudaMemcpyToSymbol(c_bessd, bd, sizeof bd));
     *out = c;
     return 0;
 }
@@ -291,6 +296,7 @@ static SolverOpts to_sopts(const torj_options* o, double s_max) {
     s.n_segments = d.n_segments; s.max_steps = d.max_steps_per_segment; s.s_max = s_max; s.dtmax = d.dtmax;
     s.abstol = d.abstol; s.reltol = d.reltol; s.psi_stop = d.psi_stop; s.p_stop = d.p_stop; s.te_min = d.te_min;
     s.max_harmonic = d.max_harmonic;
+    s.alpha_floor = d.alpha_floor;
     return s;
 }
 
@@ -305,7 +311,7 @@ int torj_probe(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
     CK(cudaMalloc(&dout, 11 * n * sizeof(double)));
     CK(cudaMemcpyAsync(dx, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dN, N, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, dout);
+    k_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, dout);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout, 11 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -323,7 +329,7 @@ int torj_rhs(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t
     CK(cudaMalloc(&d_u, 7 * n * sizeof(double)));
     CK(cudaMalloc(&d_du, 7 * n * sizeof(double)));
     CK(cudaMemcpyAsync(d_u, u, 7 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, d_du);
+    k_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, d_du);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(du, d_du, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -359,7 +365,7 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     CK(cudaMalloc(&b->d_status, n * sizeof(int)));
     CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
     CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
-    CK(cudaMalloc(&b->d_counters, 6 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_counters, 7 * sizeof(unsigned long long)));
     CK(cudaMemcpyAsync(b->d_pos, pos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(b->d_dir, dir, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(b->d_w, weight, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -412,6 +418,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (opt) od = *opt;
     if (od.scheme != 0 && od.scheme != 1) FAIL("torj_bundle_trace: scheme must be 0 (Tsit5) or 1 (OwrenZen3)");
     if (od.n_segments < 1) FAIL("torj_bundle_trace: n_segments < 1");
+    if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
     if (b->n_psi != n_psi) {
@@ -436,7 +443,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     CK(cudaStreamSynchronize(st));  // dV is a local; psi_edges belongs to the caller
     CK(cudaMemsetAsync(b->d_bins, 0, (n_psi + 2) * sizeof(double), st));
     CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(b->d_counters, 0, 6 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 7 * sizeof(unsigned long long), st));
     if (b->traj_count > 0) CK(cudaMemsetAsync(b->d_tprof, 0, (size_t)b->traj_count * n_psi * sizeof(double), st));
 
     SolverOpts so = to_sopts(&od, s_max);
@@ -486,7 +493,7 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
     if (P_dep) CK(cudaMemcpyAsync(P_dep, b->d_Pdep, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (n_points) CK(cudaMemcpyAsync(n_points, b->d_npts, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (status) CK(cudaMemcpyAsync(status, b->d_status, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    unsigned long long cn[6];
+    unsigned long long cn[7];
     CK(cudaMemcpyAsync(cn, b->d_counters, sizeof cn, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (dP_dV) memcpy(dP_dV, prof.data(), b->n_psi * sizeof(double));
@@ -494,6 +501,7 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
     if (counters) {
         counters->n_acc = (int64_t)cn[0]; counters->n_rej = (int64_t)cn[1]; counters->n_rhs = (int64_t)cn[2];
         counters->n_alpha = (int64_t)cn[3]; counters->n_harm = (int64_t)cn[4]; counters->n_rays_ok = (int64_t)cn[5];
+        counters->n_harm_pruned = (int64_t)cn[6];
     }
     return 0;
 }

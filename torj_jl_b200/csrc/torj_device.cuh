@@ -44,6 +44,7 @@ struct GLNodes {
 __constant__ GLNodes c_gl;
 // Horner coefficients of J_n(z) = (z/2)^n/n! * sum_k c[n][k] y^k, y = z^2/4 : c[n][k] = (-1)^k n! / (k! (n+k)!)
 __constant__ double c_bess[5][TORJ_BESS_K];
+__constant__ double c_bessd[5][TORJ_BESS_K];  // (n + 2k) c_bess[n][k]: series of z J_n'(z)
 
 struct RayConst {
     double omega;    // 2 pi f
@@ -52,11 +53,12 @@ struct RayConst {
     double w_over_c; // omega / c
     double moded;    // +1 X-mode, -1 O-mode
     double te_min;
+    double alpha_floor;
     int mode;
     int max_harmonic;
 };
 
-__device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te_min, int max_harmonic) {
+__device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te_min, int max_harmonic, double alpha_floor) {
     RayConst rc;
     rc.omega = 2.0 * M_PI * f;
     rc.cX = TORJ_E * TORJ_E / (TORJ_EPS0 * TORJ_ME * rc.omega * rc.omega);
@@ -66,11 +68,12 @@ __device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te
     rc.mode = mode;
     rc.te_min = te_min;
     rc.max_harmonic = max_harmonic;
+    rc.alpha_floor = alpha_floor;
     return rc;
 }
 
 struct Counters {
-    unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm;
+    unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm, n_prune;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -305,93 +308,138 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
     return N;
 }
 
-// J_{M-1}, J_M, J_{M+1} at z given hz = z/2, y = hz^2, by K-term Horner series
+// exp(x) for x <= 0, branch-free: arguments below -708 are clamped (result 3e-308 instead of a denormal/0, an
+// absolute error that cannot matter next to alpha_floor).  k = rint(x log2 e), r = x - k ln2 (two-part), degree-13
+// Taylor polynomial on |r| <= ln2/2 (remainder < 2e-17), scaled by 2^k built in the exponent field.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -708.0);
+    const double kd = rint(x * 1.4426950408889634074);
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kd;  // in [-1022, 0]
+    return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+// J_M(z) and D = z J_M'(z) by K-term Horner series in y = z^2/4 (hz = z/2):
+//   J_M = hz^M/M! sum_k c[M][k] y^k ,  z J_M' = hz^M/M! sum_k (M+2k) c[M][k] y^k
+// The reference's three Bessel functions enter abs_Al_pol_fact (src/absorption.jl:152-165) only through
+//   J_M^2,  J_M (J_{M-1} - J_{M+1}) = 2 J_M J_M',  J_{M-1} J_{M+1} = (M J_M / z)^2 - J_M'^2
+// so two series suffice and nothing is divided by z.
 template <int M, int K>
-__device__ __forceinline__ void bessel3(double hz, double y, double& Jl, double& Jn, double& Ju) {
-    const double ny = y;  // series in +y, the alternating sign lives in the coefficients
-    double sl = c_bess[M - 1][K - 1], sn = c_bess[M][K - 1], su = c_bess[M + 1][K - 1];
+__device__ __forceinline__ void bessel_JD(double hz, double y, double& J, double& D) {
+    double sj = c_bess[M][K - 1], sd = c_bessd[M][K - 1];
 #pragma unroll
     for (int k = K - 2; k >= 0; --k) {
-        sl = fma(sl, ny, c_bess[M - 1][k]);
-        sn = fma(sn, ny, c_bess[M][k]);
-        su = fma(su, ny, c_bess[M + 1][k]);
+        sj = fma(sj, y, c_bess[M][k]);
+        sd = fma(sd, y, c_bessd[M][k]);
     }
-    // (z/2)^n / n!
-    double p1 = hz, p2 = hz * hz * 0.5, p3 = p2 * hz * (1.0 / 3.0), p4 = p3 * hz * 0.25;
-    if (M == 2) { Jl = p1 * sl; Jn = p2 * sn; Ju = p3 * su; }
-    else        { Jl = p2 * sl; Jn = p3 * sn; Ju = p4 * su; }
+    double p = (M == 2) ? hz * hz * 0.5 : hz * hz * hz * (1.0 / 6.0);
+    J = p * sj;
+    D = p * sd;
 }
 
 struct HarmPre {  // per-call invariants of the harmonic integral
     double mu, omega_bar, m_0, N_par, N_perp, spar;  // spar = sqrt(1 - N_par^2)
     double Axz_sq_ey_sq, Re_Axz_ey, Re_Axz_ez, Re_ey_ez, ey_sq, ez_sq;
+    double pref;     // mu * a * (mu/2pi)^(3/2), a = 1/(1 + 105/(128 mu^2) + 15/(8 mu))
+    double to_alpha; // 2 pi^2/m_0 * X * (omega/c) / Y : c_abs -> alpha
+    double floor_;   // alpha_floor (1/m); harmonics whose rigorous upper bound is below it are skipped
 };
 
-// reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M; returns c_abs_m
+struct HarmCoef {  // per-harmonic invariants
+    double x_m, e0, e1, k1, k2, k3m2, k3, k4, k5, k6, scale;
+};
+
+// reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M
 template <int M, int K, bool GENERIC>
-__device__ __forceinline__ double harmonic_sum(const HarmPre& h, double x_m, double A /* M/m_0 */, double q /* sqrt(A^2-1) */) {
-    const double fm = (double)M;
-    // gamma is linear in t on the resonance curve: gamma = (A + N_par q t)/spar  (== sqrt(1+u_par^2+u_perp^2))
-    double g0 = A / h.spar, g1 = h.N_par * q / h.spar;
-    double e0 = h.mu * (1.0 - g0), e1 = -h.mu * g1;
-    double xs = x_m / (fm * h.spar);
-    double xm_m = x_m / fm;
-    double k1 = h.Axz_sq_ey_sq;
-    double k2 = h.Re_Axz_ey * xm_m;
-    double k3 = h.ey_sq / (fm * fm);
-    double k4 = xs * xs * h.ez_sq;
-    double k5 = 2.0 * xs * h.Re_Axz_ez;
-    double k6 = xs * h.Re_ey_ez * xm_m;
+__device__ __forceinline__ double harmonic_sum(const HarmCoef& c) {
     double sum = 0.0;
     const int n = c_gl.n;
-#pragma unroll 2
+#pragma unroll 1
     for (int k = 0; k < n; ++k) {
-        double t = c_gl.t[k], sq = c_gl.sq[k];
-        double ex = exp(fma(e1, t, e0));
-        double z = x_m * sq;
-        double Jl, Jn, Ju;
+        const double t = c_gl.t[k], sq = c_gl.sq[k];
+        const double ex = exp_nonpos(fma(c.e1, t, c.e0));
+        const double z = c.x_m * sq;
+        double J, D;
         if (GENERIC) {
-            Jl = jn(M - 1, z); Jn = jn(M, z); Ju = jn(M + 1, z);
+            J = jn(M, z);
+            D = 0.5 * z * (jn(M - 1, z) - jn(M + 1, z));
         } else {
-            double hz = 0.5 * z;
-            bessel3<M, K>(hz, hz * hz, Jl, Jn, Ju);
+            const double hz = 0.5 * z;
+            bessel_JD<M, K>(hz, hz * hz, J, D);
         }
-        double Jn2 = Jn * Jn;
-        double dsq = sq * Jn * (Jl - Ju);
-        double pf = k1 * Jn2;
-        pf = fma(k2, dsq, pf);
-        pf = fma(-k3 * z * z, Jl * Ju, pf);
-        double tJ = t * Jn2;
-        pf = fma(k4 * t, tJ, pf);
-        pf = fma(k5, tJ, pf);
-        pf = fma(k6 * t, dsq, pf);
+        const double J2 = J * J, JD = J * D;
+        double pf = c.k1 * J2;                 // (|Axz|^2 + |ey|^2) J^2
+        pf = fma(c.k2, JD, pf);                // Re(Axz ey*) x_m/m * dsq,   dsq = (2/x_m) J D
+        pf = fma(-c.k3m2, J2, pf);             // -(z/m)^2 |ey|^2 J_{m-1} J_{m+1} = -|ey|^2 (J^2 - D^2/m^2)
+        pf = fma(c.k3, D * D, pf);
+        const double tJ = t * J2;
+        pf = fma(c.k4 * t, tJ, pf);
+        pf = fma(c.k5, tJ, pf);
+        pf = fma(c.k6 * t, JD, pf);
         sum = fma(c_gl.w[k] * pf, ex, sum);
     }
-    double sc = fm / (h.N_perp * h.omega_bar);
-    double a = 1.0 / (1.0 + 105.0 / (128.0 * h.mu * h.mu) + 15.0 / (8.0 * h.mu));
-    double s = sqrt(h.mu * (0.5 / M_PI));
-    return sum * (-h.mu) * sc * sc * a * (s * s * s);
+    return sum * c.scale;
 }
 
 // rarely taken variants kept out of line so the hot code stays small (instruction cache)
 template <int M>
-__device__ __noinline__ double harmonic_sum_large(const HarmPre& h, double x_m, double A, double q) {
-    if (x_m <= 6.5) return harmonic_sum<M, 24, false>(h, x_m, A, q);
-    return harmonic_sum<M, 1, true>(h, x_m, A, q);
+__device__ __noinline__ double harmonic_sum_large(const HarmCoef& c) {
+    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false>(c);
+    return harmonic_sum<M, 1, true>(c);
 }
 
-// Series length: |term_K| = y^K n!/(K!(n+K)!) with y = x_m^2/4; K=14 is below 1e-17 for x_m <= 3.2
-// (covers the m=2 layer, x_m ~ 1, and m=3 next to it, x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
+// One harmonic's contribution to alpha [1/m] (sign included), or 0 when a rigorous bound shows it is < floor.
+// Series length: |term_K| = y^K M!/(K!(M+K)!) (x (M+2K) for D) with y = x_m^2/4: K=12 leaves < 5e-14 for
+// x_m <= 3.2 (m=2 layer: x_m ~ 1; m=3 next to it: x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
 template <int M>
-__device__ __forceinline__ double harmonic_integral(const HarmPre& h) {
+__device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt) {
     const double fm = (double)M;
-    double A = fm / h.m_0;
-    double q = sqrt(A * A - 1.0);
-    double x_m = h.N_perp * h.omega_bar * q;
-    double c;
-    if (x_m <= 3.2) c = harmonic_sum<M, 14, false>(h, x_m, A, q);
-    else c = harmonic_sum_large<M>(h, x_m, A, q);
-    return q * c;  // sqrt((m/m_0)^2 - 1) * c_abs_m, reference src/absorption.jl:218
+    const double A = fm / h.m_0;
+    const double q = sqrt(A * A - 1.0);
+    HarmCoef c;
+    c.x_m = h.N_perp * h.omega_bar * q;
+    // gamma is linear in t on the resonance curve: gamma = (A + N_par q t)/spar  (== sqrt(1 + u_par^2 + u_perp^2))
+    const double g0 = A / h.spar, g1 = h.N_par * q / h.spar;
+    c.e0 = h.mu * (1.0 - g0);
+    c.e1 = -h.mu * g1;
+    const double xs = c.x_m / (fm * h.spar);
+    c.k1 = h.Axz_sq_ey_sq;
+    c.k2 = 2.0 * h.Re_Axz_ey / fm;
+    c.k3m2 = h.ey_sq;
+    c.k3 = h.ey_sq / (fm * fm);
+    c.k4 = xs * xs * h.ez_sq;
+    c.k5 = 2.0 * xs * h.Re_Axz_ez;
+    c.k6 = 2.0 * xs * h.Re_ey_ez / fm;
+    const double sc = fm / (h.N_perp * h.omega_bar);
+    // c_abs_m * sqrt((m/m0)^2-1) and the conversion to alpha (reference src/absorption.jl:186,218-223); the
+    // reference's overall minus sign cancels the (-mu) of the integrand
+    c.scale = h.pref * sc * sc * q * h.to_alpha;
+    if (h.floor_ > 0.0) {
+        // |J_n| <= 1, |D| = |z(J_{m-1}-J_{m+1})/2| <= x_m, sum of weights = 2, exponent <= e0 + |e1|
+        const double xm = c.x_m;
+        const double pmax = fabs(c.k1) + fabs(c.k2) * xm + fabs(c.k3m2) + fabs(c.k3) * xm * xm + fabs(c.k4) + fabs(c.k5)
+                            + fabs(c.k6) * xm;
+        const double bound = 2.0 * pmax * fabs(c.scale) * exp_nonpos(fmin(0.0, c.e0 + fabs(c.e1)));
+        if (bound < h.floor_) { cnt.n_prune++; return 0.0; }
+    }
+    cnt.n_harm++;
+    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false>(c);
+    return harmonic_sum_large<M>(c);
 }
 
 // reference src/absorption.jl:191-226; omega enters only through omega/c
@@ -419,11 +467,15 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     h.Re_Axz_ey = Axz * e.ey;
     h.Re_Axz_ez = Axz * e.ez;
     h.Re_ey_ez = e.ey * e.ez;
-    double c_abs = 0.0;
-    if (2.0 >= h.m_0 && rc.max_harmonic >= 2) { cnt.n_harm++; c_abs += harmonic_integral<2>(h); }
-    if (3.0 >= h.m_0 && rc.max_harmonic >= 3) { cnt.n_harm++; c_abs += harmonic_integral<3>(h); }
-    c_abs = -(c_abs * 2.0 * M_PI * M_PI / h.m_0);
-    return c_abs * X * rc.w_over_c / Y;
+    double a = 1.0 / (1.0 + 105.0 / (128.0 * h.mu * h.mu) + 15.0 / (8.0 * h.mu));
+    double sm = sqrt(h.mu * (0.5 / M_PI));
+    h.pref = h.mu * a * (sm * sm * sm);
+    h.to_alpha = 2.0 * M_PI * M_PI / h.m_0 * X * rc.w_over_c / Y;
+    h.floor_ = rc.alpha_floor;
+    double alpha = 0.0;
+    if (2.0 >= h.m_0 && rc.max_harmonic >= 2) alpha += harmonic_alpha<2>(h, cnt);
+    if (3.0 >= h.m_0 && rc.max_harmonic >= 3) alpha += harmonic_alpha<3>(h, cnt);
+    return alpha;
 }
 
 // ------------------------------------------------------------------------------------------------

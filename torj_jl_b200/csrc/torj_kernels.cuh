@@ -19,7 +19,7 @@ __constant__ Tableau c_tab[2];
 struct SolverOpts {
     int n_segments;
     int max_steps;
-    double s_max, dtmax, abstol, reltol, psi_stop, p_stop, te_min;
+    double s_max, dtmax, abstol, reltol, psi_stop, p_stop, te_min, alpha_floor;
     int max_harmonic;
 };
 
@@ -145,7 +145,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
     double N0[3] = {B.dir[i], B.dir[n + i], B.dir[2 * n + i]};
     double f = B.per_ray_fm ? B.freq[i] : B.freq[0];
     int mode = B.per_ray_fm ? B.mode[i] : B.mode[0];
-    RayConst rc = make_ray_const(f, mode, O.te_min, O.max_harmonic);
+    RayConst rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
     int status = 0;
     B.P_final[i] = 0.0; B.P_dep[i] = 0.0; B.n_points[i] = 0;
     B.psi_launch[i] = psi_at(T, x0);
@@ -191,7 +191,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
     double Np[3];
     {
         double u[7] = {p[0], p[1], p[2], N0[0], N0[1], N0[2], 1.0}, du[7];
-        Counters c0 = {0, 0, 0, 0, 0};
+        Counters c0 = {0, 0, 0, 0, 0, 0};
         PointVals pv;
         rhs<false>(T, rc, u, du, c0, &pv);
         Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 0.0, rc.moded);
@@ -256,7 +256,7 @@ struct TraceArgs {
     const double* psi_edges;          // [n_psi]
     double* bins;                     // [n_psi] weighted shell power, [n_psi] = sum w_i P_i, [n_psi+1] = sum w_i
     unsigned long long* next_ray;     // work queue head
-    unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok
+    unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok, n_prune
 };
 
 __device__ __forceinline__ double eps_of(double x) {  // Julia eps(x)
@@ -287,11 +287,11 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
     extern __shared__ double smem[];
     double* s_edges = smem;             // [n_psi]
     double* s_bins = smem + a.n_psi;    // [n_psi]
-    __shared__ unsigned long long s_cnt[6];
+    __shared__ unsigned long long s_cnt[7];
     __shared__ double s_tot[2];
     const int n_psi = a.n_psi;
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x) { s_edges[j] = a.psi_edges[j]; s_bins[j] = 0.0; }
-    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
     __syncthreads();
 
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
     int seg = 0, npts = 0, rstat = 0;
     RayConst rc;
     DepoState dst;
-    Counters cnt = {0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0};
     double tot_dep = 0.0, tot_w = 0.0;
     unsigned int rays_ok = 0;
     long long tj = -1;  // index into the trajectory window or -1
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
                     wgt = a.B.weight[idx];
                     double f = a.B.per_ray_fm ? a.B.freq[idx] : a.B.freq[0];
                     int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
-                    rc = make_ray_const(f, mode, O.te_min, O.max_harmonic);
+                    rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
                     seg = 0; npts = 0; rstat = 0; pdep = 0.0;
                     tj = (idx >= a.J.first && idx < a.J.first + a.J.count) ? idx - a.J.first : -1;
                     // samples 1 and 2: launch point and plasma entry (reference src/solve.jl:149-153)
@@ -500,25 +500,25 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
     }
 
     // ---- block reduction: warp shuffles, shared-memory atomics, then global atomics
-    unsigned long long c6[6] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok};
+    unsigned long long c6[7] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok, cnt.n_prune};
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         tot_dep += __shfl_down_sync(FULL, tot_dep, off);
         tot_w += __shfl_down_sync(FULL, tot_w, off);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) c6[q] += __shfl_down_sync(FULL, c6[q], off);
+        for (int q = 0; q < 7; ++q) c6[q] += __shfl_down_sync(FULL, c6[q], off);
     }
     if (lane == 0) {
         atomicAdd(&s_tot[0], tot_dep);
         atomicAdd(&s_tot[1], tot_w);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) atomicAdd(&s_cnt[q], c6[q]);
+        for (int q = 0; q < 7; ++q) atomicAdd(&s_cnt[q], c6[q]);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x)
         if (s_bins[j] != 0.0) atomicAdd(&a.bins[j], s_bins[j]);
     if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
-    if (threadIdx.x < 6) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < 7) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
@@ -534,12 +534,12 @@ __global__ void k_finalize(const double* bins, const double* dV, int n_psi, doub
 // ------------------------------------------------------------------------------------------------
 // out[11][n]: psi, ne, Te, Bx, By, Bz, X, Y, N_par, Lambda, alpha
 __global__ void k_probe(DevTables T, long long n, const double* x, const double* N, double f, int mode, double te_min,
-                        int max_harmonic, double* out) {
+                        int max_harmonic, double alpha_floor, double* out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic);
+    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double u[7] = {x[i], x[n + i], x[2 * n + i], N[i], N[n + i], N[2 * n + i], 1.0}, du[7];
-    Counters c = {0, 0, 0, 0, 0};
+    Counters c = {0, 0, 0, 0, 0, 0};
     PointVals pv;
     rhs<true>(T, rc, u, du, c, &pv);
     double Babs = pv.Y / rc.cY;
@@ -552,13 +552,13 @@ __global__ void k_probe(DevTables T, long long n, const double* x, const double*
 }
 
 __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int mode, double te_min, int max_harmonic,
-                      double* du) {
+                      double alpha_floor, double* du) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic);
+    RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double uu[7], dd[7];
     for (int q = 0; q < 7; ++q) uu[q] = u[(size_t)q * n + i];
-    Counters c = {0, 0, 0, 0, 0};
+    Counters c = {0, 0, 0, 0, 0, 0};
     rhs<true>(T, rc, uu, dd, c);
     for (int q = 0; q < 7; ++q) du[(size_t)q * n + i] = dd[q];
 }
