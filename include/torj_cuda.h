@@ -86,6 +86,8 @@ void torj_ctx_destroy(torj_ctx* ctx);
 int torj_ctx_sync(torj_ctx* ctx);
 /* kernels launched by this library on ctx since creation */
 int64_t torj_ctx_launch_count(const torj_ctx* ctx);
+/* device duration (CUDA events on the context stream) of the most recent trace-kernel launch; synchronises on it */
+int torj_ctx_last_trace_ms(torj_ctx* ctx, double* ms);
 
 /* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64). */
 int torj_abs_init(torj_ctx* ctx, int32_t n, const double* nodes, const double* weights);

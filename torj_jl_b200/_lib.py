@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtorj_cuda.so")
+LIB_PATH = os.environ.get("TORJ_CUDA_LIB") or os.path.join(_HERE, "libtorj_cuda.so")  # override: tuning experiments
 _LIB = None
 
 c_dp = C.POINTER(C.c_double)
@@ -47,6 +47,7 @@ SIGNATURES = {
     "torj_ctx_destroy": (None, [c_vp]),
     "torj_ctx_sync": (C.c_int, [c_vp]),
     "torj_ctx_launch_count": (C.c_int64, [c_vp]),
+    "torj_ctx_last_trace_ms": (C.c_int, [c_vp, c_dp]),
     "torj_abs_init": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
     "torj_bspline_prefilter_2d": (C.c_int, [C.c_int32, C.c_int32, c_dp, c_dp]),
     "torj_bspline_prefilter_1d": (C.c_int, [C.c_int32, c_dp, c_dp]),

@@ -35,6 +35,8 @@ struct torj_ctx {
     bool gl_set = false;
     int num_sms = 0;
     int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the last k_trace launch
+    bool ev_valid = false;
 };
 
 struct torj_plasma {
@@ -133,6 +135,8 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
         c->own_stream = true;
     }
     CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
     Tableau t[2];
     fill_tableaux(t);
     CK(cudaMemcpyToSymbol(c_tab, t, sizeof t));
@@ -155,6 +159,8 @@ void torj_ctx_destroy(torj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
 }
 
@@ -165,6 +171,16 @@ int torj_ctx_sync(torj_ctx* c) {
 }
 
 int64_t torj_ctx_launch_count(const torj_ctx* c) { return c->launches; }
+
+int torj_ctx_last_trace_ms(torj_ctx* c, double* ms) {
+    if (!c->ev_valid) FAIL("torj_ctx_last_trace_ms: no trace launched yet");
+    if (set_device(c)) return 1;
+    CK(cudaEventSynchronize(c->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    *ms = (double)t;
+    return 0;
+}
 
 int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* weights) {
     if (n < 1 || n > TORJ_MAX_GL) FAIL("torj_abs_init: need 1 <= n <= 64");
@@ -452,7 +468,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     CK(cudaGetLastError());
 
     TraceArgs a;
-    a.T = p->T; a.Tg = p->dT; a.B = b->B; a.O = so;
+    a.T = p->T; a.B = b->B; a.O = so;
     a.J.first = b->traj_first; a.J.count = b->traj_count; a.J.max_pts = b->traj_max;
     a.J.s = b->d_ts; a.J.xyz = b->d_txyz; a.J.P = b->d_tP; a.J.dP = b->d_tdP; a.J.prof = b->d_tprof;
     a.n_psi = n_psi; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
@@ -469,10 +485,13 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     }
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
     int64_t grid = std::min<int64_t>((int64_t)c->num_sms * bps, blocks_needed);  // persistent: resident CTAs only
+    CK(cudaEventRecord(c->ev0, st));
     if (od.scheme == 0) k_trace<0><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
     else k_trace<1><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
     k_finalize<<<(n_psi + 2 + 127) / 128, 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->d_profile);
     c->launches++;
     CK(cudaGetLastError());

@@ -54,6 +54,8 @@ struct RayConst {
     double moded;    // +1 X-mode, -1 O-mode
     double te_min;
     double alpha_floor;
+    double icY;       // 1/cY
+    double ln_te_min; // log(te_min): the Te gate is applied to the spline value ln Te
     int mode;
     int max_harmonic;
 };
@@ -69,12 +71,43 @@ __device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te
     rc.te_min = te_min;
     rc.max_harmonic = max_harmonic;
     rc.alpha_floor = alpha_floor;
+    rc.icY = 1.0 / rc.cY;
+    rc.ln_te_min = log(te_min);
     return rc;
 }
 
 struct Counters {
     unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm, n_prune;
 };
+
+// ------------------------------------------------------------------------------------------------
+// Branch-free FP64 reciprocal / reciprocal square root / square root: MUFU seed (rcp/rsqrt.approx.ftz.f64, ~2^-22)
+// + two Newton steps in FMA arithmetic (error ~1 ulp).  The library's IEEE division and sqrt cost 3-4x the
+// instructions and carry a slow-path branch each; the hot path has ~25 of them per RHS.  Arguments here are
+// normal, positive (or non-zero for rcp) numbers; zero is handled where it can occur (sqrt_fast).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, 0.5 * y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-x * y, 0.5 * y, 0.5);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double sqrt_fast(double x) {  // x >= 0
+    double y = rsqrt_fast(x);
+    double s = x * y;
+    s = fma(fma(-s, s, x), 0.5 * y, s);
+    return x > 0.0 ? s : 0.0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // cubic B-spline weights; dw already divided by the grid step
@@ -236,23 +269,26 @@ struct Disp {
     double Ns2, dX, dY, dNp;
 };
 
+// iY = 1/Y is passed in (the RHS has 1/|B| already); one rsqrt and one division in total
 template <bool DERIV>
-__device__ __forceinline__ Disp refractive_index_sq(double X, double Y, double Np, double moded) {
+__device__ __forceinline__ Disp refractive_index_sq(double X, double Y, double iY, double Np, double moded) {
     Disp o;
     double Np2 = Np * Np, Y2 = Y * Y;
     double om = 1.0 - Np2;
-    double iY2 = 1.0 / Y2;
+    double iY2 = iY * iY;
     double delta = om * om + 4.0 * Np2 * (1.0 - X) * iY2;
-    double S = sqrt(delta);
+    double rS = rsqrt_fast(delta);
+    double S = delta * rS;
+    if (delta == 0.0) S = 0.0;
     double D = 2.0 * (-1.0 + X + Y2);
-    double iD = 1.0 / D;
+    double iD = rcp_fast(D);
     double G = 1.0 + moded * S + Np2;
     double H = X * Y2;
     o.Ns2 = 1.0 - X + G * iD * H;
     if (DERIV) {
-        double hS = 0.5 / S;  // dS/d. = dDelta/d. * hS
+        double hS = 0.5 * rS;  // dS/d. = dDelta/d. * hS
         double S_X = -4.0 * Np2 * iY2 * hS;
-        double S_Y = -8.0 * Np2 * (1.0 - X) * iY2 / Y * hS;
+        double S_Y = -8.0 * Np2 * (1.0 - X) * iY2 * iY * hS;
         double S_N = (-4.0 * Np * om + 8.0 * Np * (1.0 - X) * iY2) * hS;
         double GH_D2 = G * H * iD * iD;
         o.dX = -1.0 + (moded * S_X * H + G * Y2) * iD - 2.0 * GH_D2;
@@ -271,48 +307,52 @@ struct Pol {  // e = (ex, i*ey, ez) with ex, ey, ez real
     double ex, ey, ez;
 };
 
-__device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, double ct, double st, int mode, Pol& e) {
+// reference src/absorption.jl:10-64. iY = 1/Y; st2 = sin^2, ct2 = cos^2 of the propagation angle.
+// 3 sqrt/rsqrt + 2 divisions (the reference's sqrt(1/(N sqrt(.))) is one rsqrt here).
+__device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, double iY, double ct, double st, double ct2,
+                                                        double st2, int mode, Pol& e) {
     e.ex = e.ey = e.ez = 0.0;
     if (X >= 1.0) return 0.0;
-    double st2 = st * st, ct2 = ct * ct, Y2 = Y * Y;
+    double Y2 = Y * Y;
     double omX = 1.0 - X;
     double rho = Y2 * st2 * st2 + 4.0 * omX * omX * ct2;
     if (rho < 0.0) return 0.0;
-    rho = sqrt(rho);
-    double f = (2.0 * omX) / (2.0 * omX - Y2 * st2 - (double)mode * Y * rho);
-    double N = 1.0 - X * f;
-    if (N < 0.0) return 0.0;
-    N = sqrt(N);
+    rho = sqrt_fast(rho);
+    double f = (2.0 * omX) * rcp_fast(2.0 * omX - Y2 * st2 - (double)mode * Y * rho);
+    double N2 = 1.0 - X * f;
+    if (N2 < 0.0) return 0.0;
+    double N = sqrt_fast(N2);
     double h = 1.0 - (1.0 - Y2) * f;
-    double g = h / Y;
+    double g = h * iY;
     if (ct2 < 1e-5 || 1.0 - st2 < 1e-5) {
         if (mode > 0) {
-            e.ey = sqrt(1.0 / N);
+            e.ey = rsqrt_fast(N);
             e.ex = -g * e.ey;
         } else {
-            e.ez = sqrt(1.0 / N);
+            e.ez = rsqrt_fast(N);
         }
     } else {
-        double N2 = N * N;
         double den = omX - N2 * st2;
-        double hy = h * h / Y2;
-        double a_in = 1.0 + ((omX * N2 * ct2) / (den * den)) * hy;
+        double iden = rcp_fast(den);
+        double hy = g * g;  // (1/Y^2) (1 - (1 - Y^2) f)^2
+        double a_in = 1.0 + (omX * N2 * ct2) * (iden * iden) * hy;
         double a_sq = st2 * a_in * a_in;
-        double b_in = 1.0 + (omX / den) * hy;
+        double b_in = 1.0 + (omX * iden) * hy;
         double b_sq = ct2 * b_in * b_in;
-        double ey = sqrt(1.0 / (N * sqrt(a_sq + b_sq)));
+        double ey = rsqrt_fast(N * sqrt_fast(a_sq + b_sq));
         e.ey = mode > 0 ? ey : -ey;
-        e.ex = -g * e.ey;                           // i*g * (i*ey)
-        e.ez = -((N2 * st * ct) / den) * e.ex;
+        e.ex = -g * e.ey;  // i g * (i ey)
+        e.ez = -((N2 * st * ct) * iden) * e.ex;
     }
     return N;
 }
 
-// exp(x) for x <= 0, branch-free: arguments below -708 are clamped (result 3e-308 instead of a denormal/0, an
-// absolute error that cannot matter next to alpha_floor).  k = rint(x log2 e), r = x - k ln2 (two-part), degree-13
-// Taylor polynomial on |r| <= ln2/2 (remainder < 2e-17), scaled by 2^k built in the exponent field.
-__device__ __forceinline__ double exp_nonpos(double x) {
-    x = fmax(x, -708.0);
+// exp(x), branch-free, for |x| <= 708 (clamped outside: the callers' arguments are ln n_e ~ 40..46, -ln T_e and
+// non-positive exponents whose values below e^-708 cannot matter next to alpha_floor).
+// k = rint(x log2 e), r = x - k ln2 (two-part), degree-13 Taylor polynomial on |r| <= ln2/2 (remainder < 4e-18),
+// scaled by 2^k built in the exponent field.
+__device__ __forceinline__ double exp_fast(double x) {
+    x = fmin(fmax(x, -708.0), 708.0);
     const double kd = rint(x * 1.4426950408889634074);
     double r = fma(kd, -6.93147180369123816490e-01, x);
     r = fma(kd, -1.90821492927058770002e-10, r);
@@ -330,7 +370,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const int k = (int)kd;  // in [-1022, 0]
+    const int k = (int)kd;  // in [-1022, 1022]
     return p * __hiloint2double((k + 1023) << 20, 0);
 }
 
@@ -353,10 +393,11 @@ __device__ __forceinline__ void bessel_JD(double hz, double y, double& J, double
 }
 
 struct HarmPre {  // per-call invariants of the harmonic integral
-    double mu, omega_bar, m_0, N_par, N_perp, spar;  // spar = sqrt(1 - N_par^2)
+    double mu, Y, iY, N_par, N_perp, spar, ispar;  // spar = sqrt(1 - N_par^2)
     double Axz_sq_ey_sq, Re_Axz_ey, Re_Axz_ez, Re_ey_ez, ey_sq, ez_sq;
+    double iNp2;     // 1 / N_perp^2
     double pref;     // mu * a * (mu/2pi)^(3/2), a = 1/(1 + 105/(128 mu^2) + 15/(8 mu))
-    double to_alpha; // 2 pi^2/m_0 * X * (omega/c) / Y : c_abs -> alpha
+    double to_alpha; // 2 pi^2/m_0 * X * (omega/c) / Y = 2 pi^2 X (omega/c) / spar : c_abs -> alpha
     double floor_;   // alpha_floor (1/m); harmonics whose rigorous upper bound is below it are skipped
 };
 
@@ -372,7 +413,7 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c) {
 #pragma unroll 1
     for (int k = 0; k < n; ++k) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
-        const double ex = exp_nonpos(fma(c.e1, t, c.e0));
+        const double ex = exp_fast(fma(c.e1, t, c.e0));
         const double z = c.x_m * sq;
         double J, D;
         if (GENERIC) {
@@ -406,35 +447,35 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef& c) {
 // One harmonic's contribution to alpha [1/m] (sign included), or 0 when a rigorous bound shows it is < floor.
 // Series length: |term_K| = y^K M!/(K!(M+K)!) (x (M+2K) for D) with y = x_m^2/4: K=12 leaves < 5e-14 for
 // x_m <= 3.2 (m=2 layer: x_m ~ 1; m=3 next to it: x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
+// One sqrt per harmonic; everything else is products of the reciprocals prepared in abs_albajar.
 template <int M>
 __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt) {
-    const double fm = (double)M;
-    const double A = fm / h.m_0;
-    const double q = sqrt(A * A - 1.0);
+    const double fm = (double)M, ifm = 1.0 / (double)M;
+    const double A = fm * h.Y * h.ispar;  // m / m_0, m_0 = spar / Y
+    const double q = sqrt_fast(fmax(A * A - 1.0, 0.0));
     HarmCoef c;
-    c.x_m = h.N_perp * h.omega_bar * q;
+    c.x_m = h.N_perp * h.iY * q;
     // gamma is linear in t on the resonance curve: gamma = (A + N_par q t)/spar  (== sqrt(1 + u_par^2 + u_perp^2))
-    const double g0 = A / h.spar, g1 = h.N_par * q / h.spar;
+    const double g0 = A * h.ispar, g1 = h.N_par * q * h.ispar;
     c.e0 = h.mu * (1.0 - g0);
     c.e1 = -h.mu * g1;
-    const double xs = c.x_m / (fm * h.spar);
+    const double xs = c.x_m * h.ispar * ifm;
     c.k1 = h.Axz_sq_ey_sq;
-    c.k2 = 2.0 * h.Re_Axz_ey / fm;
+    c.k2 = 2.0 * ifm * h.Re_Axz_ey;
     c.k3m2 = h.ey_sq;
-    c.k3 = h.ey_sq / (fm * fm);
+    c.k3 = h.ey_sq * (ifm * ifm);
     c.k4 = xs * xs * h.ez_sq;
     c.k5 = 2.0 * xs * h.Re_Axz_ez;
-    c.k6 = 2.0 * xs * h.Re_ey_ez / fm;
-    const double sc = fm / (h.N_perp * h.omega_bar);
-    // c_abs_m * sqrt((m/m0)^2-1) and the conversion to alpha (reference src/absorption.jl:186,218-223); the
-    // reference's overall minus sign cancels the (-mu) of the integrand
-    c.scale = h.pref * sc * sc * q * h.to_alpha;
+    c.k6 = 2.0 * ifm * xs * h.Re_ey_ez;
+    // (m/(N_perp omega_bar))^2 * c_abs_m * sqrt((m/m0)^2-1) and the conversion to alpha (reference
+    // src/absorption.jl:165,186,218-223); the reference's overall minus sign cancels the (-mu) of the integrand
+    c.scale = h.pref * (fm * fm * h.Y * h.Y * h.iNp2) * q * h.to_alpha;
     if (h.floor_ > 0.0) {
-        // |J_n| <= 1, |D| = |z(J_{m-1}-J_{m+1})/2| <= x_m, sum of weights = 2, exponent <= e0 + |e1|
+        // |J_n| <= 1, |D| = |z (J_{m-1} - J_{m+1})/2| <= x_m, sum of weights = 2, exponent <= e0 + |e1|
         const double xm = c.x_m;
         const double pmax = fabs(c.k1) + fabs(c.k2) * xm + fabs(c.k3m2) + fabs(c.k3) * xm * xm + fabs(c.k4) + fabs(c.k5)
                             + fabs(c.k6) * xm;
-        const double bound = 2.0 * pmax * fabs(c.scale) * exp_nonpos(fmin(0.0, c.e0 + fabs(c.e1)));
+        const double bound = 2.0 * pmax * fabs(c.scale) * exp_fast(fmin(0.0, c.e0 + fabs(c.e1)));
         if (bound < h.floor_) { cnt.n_prune++; return 0.0; }
     }
     cnt.n_harm++;
@@ -442,44 +483,54 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     return harmonic_sum_large<M>(c);
 }
 
-// reference src/absorption.jl:191-226; omega enters only through omega/c
-__device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double N_abs, double N_par, double Te,
-                                              Counters& cnt) {
-    if (Te < rc.te_min) return 0.0;
+// reference src/absorption.jl:191-226 (+ the T_e evaluation of :233). omega enters only through omega/c.
+// N2 = |N|^2, iY = 1/Y, lnTe = spline value (T_e = exp(lnTe), reference src/plasma.jl:87-89).
+__device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double iY, double N2, double N_par,
+                                              double lnTe, Counters& cnt) {
+    if (lnTe < rc.ln_te_min) return 0.0;  // Te < te_min
     cnt.n_alpha++;
     HarmPre h;
-    h.mu = TORJ_ME * TORJ_C * TORJ_C / (TORJ_E * Te);
-    h.omega_bar = 1.0 / Y;
-    double ct = N_par / N_abs;
-    double st = sqrt(fmax(0.0, (1.0 - ct) * (1.0 + ct)));  // sin(acos(ct))
-    h.N_perp = sqrt(N_abs * N_abs - N_par * N_par);
+    const double Te = exp_fast(lnTe);
+    h.mu = (TORJ_ME * TORJ_C * TORJ_C / TORJ_E) * rcp_fast(Te);
+    h.Y = Y; h.iY = iY;
+    const double iNabs = rsqrt_fast(N2);
+    const double ct = N_par * iNabs;
+    const double ct2 = ct * ct;
+    const double st2 = fmax(0.0, (1.0 - ct) * (1.0 + ct));
+    const double st = sqrt_fast(st2);                       // sin(acos(ct))
+    h.N_perp = (N2 * iNabs) * st;                           // sqrt(N_abs^2 - N_par^2)
     h.N_par = N_par;
     Pol e;
-    double N_test = abs_Al_N_with_pol_vec(X, Y, ct, st, rc.mode, e);
+    double N_test = abs_Al_N_with_pol_vec(X, Y, iY, ct, st, ct2, st2, rc.mode, e);
     if (!(N_test > 0.0) || N_test > 1.0) return 0.0;  // also catches NaN
-    h.spar = sqrt(1.0 - N_par * N_par);
-    h.m_0 = h.spar * h.omega_bar;
-    double N_eff = (h.N_perp * N_par) / (1.0 - N_par * N_par);
-    double Axz = e.ex + N_eff * e.ez;
+    const double sp2 = 1.0 - N_par * N_par;
+    h.ispar = rsqrt_fast(sp2);
+    h.spar = sp2 * h.ispar;
+    const double m_0 = h.spar * iY;
+    const double N_eff = (h.N_perp * N_par) * (h.ispar * h.ispar);
+    const double Axz = e.ex + N_eff * e.ez;
     h.ey_sq = e.ey * e.ey;
     h.ez_sq = e.ez * e.ez;
     h.Axz_sq_ey_sq = Axz * Axz + h.ey_sq;
     h.Re_Axz_ey = Axz * e.ey;
     h.Re_Axz_ez = Axz * e.ez;
     h.Re_ey_ez = e.ey * e.ez;
-    double a = 1.0 / (1.0 + 105.0 / (128.0 * h.mu * h.mu) + 15.0 / (8.0 * h.mu));
-    double sm = sqrt(h.mu * (0.5 / M_PI));
+    h.iNp2 = rcp_fast(h.N_perp * h.N_perp);
+    const double mu2 = h.mu * h.mu;
+    const double a = mu2 * rcp_fast(mu2 + 105.0 / 128.0 + (15.0 / 8.0) * h.mu);  // 1/(1 + 105/(128 mu^2) + 15/(8 mu))
+    const double sm = sqrt_fast(h.mu * (0.5 / M_PI));
     h.pref = h.mu * a * (sm * sm * sm);
-    h.to_alpha = 2.0 * M_PI * M_PI / h.m_0 * X * rc.w_over_c / Y;
+    h.to_alpha = 2.0 * M_PI * M_PI * X * rc.w_over_c * h.ispar;
     h.floor_ = rc.alpha_floor;
     double alpha = 0.0;
-    if (2.0 >= h.m_0 && rc.max_harmonic >= 2) alpha += harmonic_alpha<2>(h, cnt);
-    if (3.0 >= h.m_0 && rc.max_harmonic >= 3) alpha += harmonic_alpha<3>(h, cnt);
+    if (2.0 >= m_0 && rc.max_harmonic >= 2) alpha += harmonic_alpha<2>(h, cnt);
+    if (3.0 >= m_0 && rc.max_harmonic >= 3) alpha += harmonic_alpha<3>(h, cnt);
     return alpha;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Hamiltonian RHS: reference src/solve.jl:85-95 (gradΛ!) with analytic gradients
+// 4 rsqrt + 1 division + 2 exp outside the absorption coefficient.
 // ------------------------------------------------------------------------------------------------
 struct PointVals {
     double X, Y, N_par, b[3], Te, Lambda;
@@ -489,60 +540,54 @@ template <bool WITH_ALPHA>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
                                     PointVals* pv = nullptr) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
-    double R = sqrt(fma(x, x, y * y));
-    double iR = 1.0 / R;
-    double c = x * iR, s = y * iR;
+    const double R2 = fma(x, x, y * y);
+    const double iR = rsqrt_fast(R2);
+    const double R = R2 * iR;
+    const double c = x * iR, s = y * iR;
     Fields f;
     eval_fields(T, R, z, f);
-    double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
-    double Babs = sqrt(B2);
-    double iB = 1.0 / Babs;
-    double NR = Nx * c + Ny * s, Nph = -Nx * s + Ny * c;
-    double NB = NR * f.BR + Nph * f.Bp + Nz * f.BZ;
-    double Np = NB * iB;
-    double bx = (f.BR * c - f.Bp * s) * iB, by = (f.BR * s + f.Bp * c) * iB, bz = f.BZ * iB;
-    double X = rc.cX * exp(f.L);
-    double Y = rc.cY * Babs;
-    Disp d = refractive_index_sq<true>(X, Y, Np, rc.moded);
+    const double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
+    const double iB = rsqrt_fast(B2);
+    const double Babs = B2 * iB;
+    const double NR = Nx * c + Ny * s, Nph = -Nx * s + Ny * c;
+    const double NB = NR * f.BR + Nph * f.Bp + Nz * f.BZ;
+    const double Np = NB * iB;
+    const double bx = (f.BR * c - f.Bp * s) * iB, by = (f.BR * s + f.Bp * c) * iB, bz = f.BZ * iB;
+    const double X = rc.cX * exp_fast(f.L);
+    const double Y = rc.cY * Babs;
+    const double iY = rc.icY * iB;
+    Disp d = refractive_index_sq<true>(X, Y, iY, Np, rc.moded);
     // cylindrical gradients of X, Y, N_par at fixed N
-    double X_R = X * f.L_R, X_Z = X * f.L_Z;
-    double Bab_R = (f.BR * f.BR_R + f.Bp * f.Bp_R + f.BZ * f.BZ_R) * iB;
-    double Bab_Z = (f.BR * f.BR_Z + f.Bp * f.Bp_Z + f.BZ * f.BZ_Z) * iB;
-    double Y_R = rc.cY * Bab_R, Y_Z = rc.cY * Bab_Z;
-    double NB_R = NR * f.BR_R + Nph * f.Bp_R + Nz * f.BZ_R;
-    double NB_Z = NR * f.BR_Z + Nph * f.Bp_Z + Nz * f.BZ_Z;
-    double Np_R = (NB_R - Np * Bab_R) * iB;
-    double Np_Z = (NB_Z - Np * Bab_Z) * iB;
-    double Np_ph = (Nph * f.BR - NR * f.Bp) * iB;
-    double gR = -(d.dX * X_R + d.dY * Y_R + d.dNp * Np_R);
-    double gZ = -(d.dX * X_Z + d.dY * Y_Z + d.dNp * Np_Z);
-    double gph = -(d.dNp * Np_ph) * iR;
-    double gx = c * gR - s * gph, gy = s * gR + c * gph, gz = gZ;
-    double hx = 2.0 * Nx - bx * d.dNp, hy = 2.0 * Ny - by * d.dNp, hz = 2.0 * Nz - bz * d.dNp;
-    double inorm = 1.0 / sqrt(hx * hx + hy * hy + hz * hz);
+    const double X_R = X * f.L_R, X_Z = X * f.L_Z;
+    const double Bab_R = (f.BR * f.BR_R + f.Bp * f.Bp_R + f.BZ * f.BZ_R) * iB;
+    const double Bab_Z = (f.BR * f.BR_Z + f.Bp * f.Bp_Z + f.BZ * f.BZ_Z) * iB;
+    const double Y_R = rc.cY * Bab_R, Y_Z = rc.cY * Bab_Z;
+    const double NB_R = NR * f.BR_R + Nph * f.Bp_R + Nz * f.BZ_R;
+    const double NB_Z = NR * f.BR_Z + Nph * f.Bp_Z + Nz * f.BZ_Z;
+    const double Np_R = (NB_R - Np * Bab_R) * iB;
+    const double Np_Z = (NB_Z - Np * Bab_Z) * iB;
+    const double Np_ph = (Nph * f.BR - NR * f.Bp) * iB;
+    const double gR = -(d.dX * X_R + d.dY * Y_R + d.dNp * Np_R);
+    const double gZ = -(d.dX * X_Z + d.dY * Y_Z + d.dNp * Np_Z);
+    const double gph = -(d.dNp * Np_ph) * iR;
+    const double gx = c * gR - s * gph, gy = s * gR + c * gph, gz = gZ;
+    const double hx = 2.0 * Nx - bx * d.dNp, hy = 2.0 * Ny - by * d.dNp, hz = 2.0 * Nz - bz * d.dNp;
+    const double inorm = rsqrt_fast(hx * hx + hy * hy + hz * hz);
     du[0] = hx * inorm; du[1] = hy * inorm; du[2] = hz * inorm;
     du[3] = -gx * inorm; du[4] = -gy * inorm; du[5] = -gz * inorm;
-    double N2 = Nx * Nx + Ny * Ny + Nz * Nz;
+    const double N2 = Nx * Nx + Ny * Ny + Nz * Nz;
     if (WITH_ALPHA) {
-        double Te = exp(f.lnTe);
-        double alpha = abs_albajar(rc, X, Y, sqrt(N2), Np, Te, cnt);
+        const double alpha = abs_albajar(rc, X, Y, iY, N2, Np, f.lnTe, cnt);
         du[6] = -u[6] * alpha;
-        if (pv) pv->Te = Te;
     } else {
         du[6] = 0.0;
     }
     cnt.n_rhs++;
     if (pv) {
         pv->X = X; pv->Y = Y; pv->N_par = Np; pv->b[0] = bx; pv->b[1] = by; pv->b[2] = bz;
+        pv->Te = exp(f.lnTe);
         pv->Lambda = N2 - d.Ns2;
     }
-}
-
-// single out-of-line copy for the integrator: every stage of every step calls this one body
-__device__ __noinline__ void rhs_call(const DevTables* __restrict__ Tp, const RayConst* rcp, const double* u, double* du,
-                                      Counters* cnt) {
-    DevTables T = *Tp;
-    rhs<true>(T, *rcp, u, du, *cnt);
 }
 
 // ------------------------------------------------------------------------------------------------

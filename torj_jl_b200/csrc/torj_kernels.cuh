@@ -119,7 +119,7 @@ __device__ inline void refraction_equations(const double N[3], double X, double 
                                             const double b[3], double moded, double F[3], double (*J)[3]) {
     double ndN = -(n[0] * n0[0] + n[1] * n0[1] + n[2] * n0[2]);
     double Np = N[0] * b[0] + N[1] * b[1] + N[2] * b[2];
-    Disp d = refractive_index_sq<true>(X, Y, Np, moded);
+    Disp d = refractive_index_sq<true>(X, Y, 1.0 / Y, Np, moded);
     double Ns = sqrt(d.Ns2);
     double coef = 1.0 / Ns * ndN - sqrt(1.0 - 1.0 / (Ns * Ns) * (1.0 - ndN * ndN));
     for (int k = 0; k < 3; ++k) {
@@ -194,7 +194,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         Counters c0 = {0, 0, 0, 0, 0, 0};
         PointVals pv;
         rhs<false>(T, rc, u, du, c0, &pv);
-        Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 0.0, rc.moded);
+        Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 1.0 / pv.Y, 0.0, rc.moded);
         if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; return; }
         double N_est = sqrt(d0.Ns2);
         double R = sqrt(p[0] * p[0] + p[1] * p[1]);
@@ -248,7 +248,6 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
 // ------------------------------------------------------------------------------------------------
 struct TraceArgs {
     DevTables T;
-    const DevTables* Tg;  // the same tables descriptor in global memory (for the out-of-line RHS)
     BundleDev B;
     SolverOpts O;
     TrajDev J;
@@ -271,17 +270,30 @@ __device__ __forceinline__ double rms7(const double v[7]) {
     return sqrt(s / 7.0);
 }
 
+// pow() expands to ~150 instructions with slow paths; the controller needs it only on rejected / shrinking steps,
+// so one out-of-line copy keeps the hot loop small
+__device__ __noinline__ double pow_nl(double x, double y) { return pow(x, y); }
+
 template <int SCH>
 struct Scheme;
 template <> struct Scheme<0> { static constexpr int S = 7; static constexpr int ORDER = 5; };
 template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int ORDER = 3; };
 
 #define TORJ_TPB 128
+#ifndef TORJ_MINB
+#define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
+#endif
 // per-ray status codes of include/torj_cuda.h: everything but OK(0) and TRAJ_TRUNCATED(6) ends the ray
 #define TORJ_FATAL(s) ((s) != 0 && (s) != 6)
 
+// Integrator phases. Every trip of the kernel's main loop evaluates the RHS exactly once per lane that holds a
+// ray, whatever that lane's phase, so the expensive code is always warp-converged; the cheap phase-specific
+// bookkeeping after it is the only divergent part. A lane that retires its ray draws a new one on the next trip.
+enum { PH_IDLE = 0, PH_SEED = 1, PH_INITDT = 2, PH_STAGE = 3, PH_CALLBACK = 4 };
+enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT = 3, ACT_AFTER_ACCEPT = 4 };
+
 template <int SCH>
-__global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
+__global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
     extern __shared__ double smem[];
@@ -289,34 +301,43 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
     double* s_bins = smem + a.n_psi;    // [n_psi]
     __shared__ unsigned long long s_cnt[7];
     __shared__ double s_tot[2];
+    __shared__ double s_a[7][7], s_bt[7];
     const int n_psi = a.n_psi;
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x) { s_edges[j] = a.psi_edges[j]; s_bins[j] = 0.0; }
     if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
+    if (threadIdx.x < 49) s_a[threadIdx.x / 7][threadIdx.x % 7] = c_tab[SCH].a[threadIdx.x / 7][threadIdx.x % 7];
+    if (threadIdx.x < 7) s_bt[threadIdx.x] = c_tab[SCH].bt[threadIdx.x];
     __syncthreads();
 
-    const DevTables& T = a.T;
+    const DevTables T = a.T;
     const SolverOpts& O = a.O;
     const long long n = a.B.n_rays;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
-    const Tableau& tb = c_tab[SCH];
     const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
+    // EEst below this always gives q <= 1 (qold >= qoldinit): (gamma*qoldinit^beta2)^(1/beta1)
+    const double eest_noshrink = pow(gamma_c * pow(qoldinit, beta2), 1.0 / beta1);
     const double s_step = O.s_max / (double)O.n_segments;
 
     // per-lane ray state
-    long long ray = -1;  // -1: needs a ray, -2: queue exhausted
-    double u[7], k[S][7];
+    long long ray = -1;
+    int phase = PH_IDLE, st = 0;
+    bool exhausted = false;
+    double u[7], tmp[7], k[S][7];
     double s0 = 0.0, wgt = 0.0, pdep = 0.0;
-    double psi_cur = 0.0, dpsi_cur = 0.0;
-    int seg = 0, npts = 0, rstat = 0;
-    RayConst rc;
-    DepoState dst;
+    double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0, dt0 = 0.0, d1 = 0.0;
+    double psi_cur = 0.0, dpsi_cur = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
+    int seg = 0, npts = 0, rstat = 0, nstep = 0;
+    RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
+    DepoState dst = {0, 0, 1.0};
     Counters cnt = {0, 0, 0, 0, 0, 0};
     double tot_dep = 0.0, tot_w = 0.0;
     unsigned int rays_ok = 0;
     long long tj = -1;  // index into the trajectory window or -1
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { u[i] = 0.0; tmp[i] = 0.0; }
 
     auto sink = [&](int shell, double dP) {
         atomicAdd(&s_bins[shell], wgt * dP);
@@ -338,23 +359,21 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
     };
 
     for (;;) {
-        // ---- warp-ballot retire-and-refill: lanes without a ray draw the next indices from the global queue
-        unsigned need = __ballot_sync(FULL, ray == -1);
+        // ---- warp-ballot retire-and-refill: idle lanes draw the next ray indices from the global queue
+        unsigned need = __ballot_sync(FULL, phase == PH_IDLE && !exhausted);
         if (need) {
             int leader = __ffs(need) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(a.next_ray, (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, leader);
-            if (ray == -1) {
+            if (phase == PH_IDLE && !exhausted) {
                 long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
                 if (idx >= n) {
-                    ray = -2;
-                } else if (a.B.status[idx] != 0) {
-                    ray = -1;  // init failed: outputs already written by k_ray_init; draw again next round
-                } else {
+                    exhausted = true;
+                } else if (a.B.status[idx] == 0) {  // failed initialisations were reported by k_ray_init
                     ray = idx;
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) u[i] = a.B.u0[(size_t)i * n + idx];
+                    for (int i = 0; i < 7; ++i) { u[i] = a.B.u0[(size_t)i * n + idx]; tmp[i] = u[i]; }
                     s0 = a.B.s0[idx];
                     wgt = a.B.weight[idx];
                     double f = a.B.per_ray_fm ? a.B.freq[idx] : a.B.freq[0];
@@ -366,135 +385,180 @@ __global__ void __launch_bounds__(TORJ_TPB) k_trace(TraceArgs a) {
                     double xl[3] = {a.B.pos[idx], a.B.pos[n + idx], a.B.pos[2 * n + idx]};
                     put_point(0.0, xl, 1.0, 0.0);
                     put_point(s0, u, 1.0, 0.0);
-                    // derivative at entry (FSAL seed) and psi there
-                    rhs_call(a.Tg, &rc, u, k[0], &cnt);
-                    double R = sqrt(u[0] * u[0] + u[1] * u[1]), pR, pZ;
-                    eval_psi(T, R, u[2], &psi_cur, &pR, &pZ);
-                    dpsi_cur = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
-                    // vacuum leg launch -> entry: P = 1, straight line
-                    double psl = a.B.psi_launch[idx];
-                    dst.shell = locate_shell(s_edges, n_psi, psl);
-                    dst.valid = 0; dst.P_last = 1.0;
-                    double dlin = (psi_cur - psl) / s0;
-                    depo_step(dst, s_edges, n_psi, s0, psl, psi_cur, dlin, dlin, 1.0, 1.0, 0.0, 0.0, sink);
+                    phase = PH_SEED;
                 }
             }
         }
-        if (__all_sync(FULL, ray == -2)) break;
-        const bool act = ray >= 0;
+        if (__all_sync(FULL, phase == PH_IDLE && exhausted)) break;
 
-        // ---- one segment = one fresh ODEProblem of the reference (src/solve.jl:155-161)
-        double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit;
-        int nstep = 0;
-        if (act) {
-            seg++;
-            t = (double)(seg - 1) * s_step + s0;
-            tstop = (double)seg * s_step + s0;
-            // initial dt: OrdinaryDiffEq ode_determine_initdt (Hairer); k[0] = f(u) is the FSAL derivative
-            double sk[7], v0[7], v1[7];
+        // ---- the one RHS evaluation of this trip (reference src/solve.jl:85-95), warp-converged
+        double out[7];
+        if (phase != PH_IDLE) rhs<true>(T, rc, tmp, out, cnt);
+
+        // ---- phase bookkeeping
+        int act = ACT_NONE;
+        if (phase == PH_SEED) {
+            // derivative at entry (FSAL seed), psi there, and the vacuum leg launch -> entry (P = 1, straight line)
 #pragma unroll
-            for (int i = 0; i < 7; ++i) { sk[i] = O.abstol + fabs(u[i]) * O.reltol; v0[i] = u[i] / sk[i]; v1[i] = k[0][i] / sk[i]; }
-            double d0 = rms7(v0), d1 = rms7(v1);
-            const double smalldt = 1e-6;
-            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
-            dt0 = fmin(dt0, O.dtmax);
-            if (dt0 < 10.0 * 2.220446049250313e-16) {
-                dt = smalldt;
-            } else {
-                double u1[7], f1[7];
+            for (int i = 0; i < 7; ++i) k[0][i] = out[i];
+            double R = sqrt(u[0] * u[0] + u[1] * u[1]), pR, pZ;
+            eval_psi(T, R, u[2], &psi_cur, &pR, &pZ);
+            dpsi_cur = pR * (u[0] * out[0] + u[1] * out[1]) / R + pZ * out[2];
+            double psl = a.B.psi_launch[ray];
+            dst.shell = locate_shell(s_edges, n_psi, psl);
+            dst.valid = 0; dst.P_last = 1.0;
+            double dlin = (psi_cur - psl) / s0;
+            depo_step(dst, s_edges, n_psi, s0, psl, psi_cur, dlin, dlin, 1.0, 1.0, 0.0, 0.0, sink);
+            act = ACT_BEGIN_SEGMENT;
+        } else if (phase == PH_INITDT) {
+            // second half of OrdinaryDiffEq's ode_determine_initdt (Hairer): out = f(u + dt0 f0)
+            double v[7];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) u1[i] = u[i] + dt0 * k[0][i];
-                rhs_call(a.Tg, &rc, u1, f1, &cnt);
+            for (int i = 0; i < 7; ++i) v[i] = (out[i] - k[0][i]) / (O.abstol + fabs(u[i]) * O.reltol);
+            double d2 = rms7(v) / dt0;
+            double md = fmax(d1, d2);
+            // 10^(-(2 + log10 md)/order) = (100 md)^(-1/order)
+            double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow_nl(100.0 * md, -1.0 / (double)ORDER);
+            dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
+            act = ACT_BEGIN_STEP;
+        } else if (phase == PH_STAGE) {
 #pragma unroll
-                for (int i = 0; i < 7; ++i) v0[i] = (f1[i] - k[0][i]) / sk[i];
-                double d2 = rms7(v0) / dt0;
-                double md = fmax(d1, d2);
-                double dt1 = (md <= 1e-15) ? fmax(smalldt, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(md)) / (double)ORDER);
-                dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
-            }
-        }
-        // ---- step loop, warp-uniform trip count so lanes reconverge every step
-        while (__any_sync(FULL, act && !TORJ_FATAL(rstat) && t < tstop)) {
-            if (act && !TORJ_FATAL(rstat) && t < tstop) {
-                if (++nstep > O.max_steps) { rstat = 4;  // TORJ_RAY_MAX_STEPS
-                    continue; }
-                dt = fmin(dt, tstop - t);
-                double tmp[7];
+            for (int i = 0; i < 7; ++i) k[st][i] = out[i];
+            if (st < S - 1) {
+                st++;
 #pragma unroll
-                for (int st = 1; st < S; ++st) {
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int j = 0; j < st; ++j) acc = fma(tb.a[st][j], k[j][i], acc);
-                        tmp[i] = fma(dt, acc, u[i]);
-                    }
-                    rhs_call(a.Tg, &rc, tmp, k[st], &cnt);
+                for (int i = 0; i < 7; ++i) {
+                    double acc = 0.0;
+                    for (int j = 0; j < st; ++j) acc = fma(s_a[st][j], k[j][i], acc);
+                    tmp[i] = fma(dt, acc, u[i]);
                 }
+            } else {
+                // tmp is the proposed new state (FSAL); embedded error estimate and PI controller
                 double at[7];
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
                     double ut = 0.0;
 #pragma unroll
-                    for (int j = 0; j < S; ++j) ut = fma(tb.bt[j], k[j][i], ut);
+                    for (int j = 0; j < S; ++j) ut = fma(s_bt[j], k[j][i], ut);
                     ut *= dt;
                     at[i] = ut / (O.abstol + fmax(fabs(u[i]), fabs(tmp[i])) * O.reltol);
                     if (!(tmp[i] == tmp[i])) bad = true;
                 }
-                if (bad) { rstat = 5;  // TORJ_RAY_NAN
-                    continue; }
-                double EEst = rms7(at);
-                double qq, q11 = 0.0;
-                if (EEst == 0.0) qq = 1.0 / qmax;
-                else {
-                    q11 = pow(EEst, beta1);
-                    qq = q11 / pow(qold, beta2);
-                    qq = fmax(1.0 / qmax, fmin(1.0 / qmin, qq / gamma_c));
-                }
-                if (EEst <= 1.0) {
-                    cnt.n_acc++;
-                    qold = fmax(EEst, qoldinit);
-                    double dtnew = dt / qq;
-                    double ttmp = t + dt;
-                    if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
-                    const double h = ttmp - t;
-                    const double P_a = u[6], dP_a = k[0][6];
-                    t = ttmp;
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) { u[i] = tmp[i]; k[0][i] = k[S - 1][i]; }
-                    if (u[6] < 0.0) {  // positivity callback (reference src/solve.jl:78-83,159-160)
-                        u[6] = 0.0;
-                        rhs_call(a.Tg, &rc, u, k[0], &cnt);
-                    }
-                    put_point(t, u, u[6], -k[0][6]);
-                    // streaming deposition over this step
-                    double R = sqrt(u[0] * u[0] + u[1] * u[1]), psi_b, pR, pZ;
-                    eval_psi(T, R, u[2], &psi_b, &pR, &pZ);
-                    double dpsi_b = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
-                    depo_step(dst, s_edges, n_psi, h, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, k[0][6], sink);
-                    psi_cur = psi_b; dpsi_cur = dpsi_b;
-                    dt = fmin(O.dtmax, dtnew);
+                if (bad) {
+                    rstat = 5;  // TORJ_RAY_NAN
+                    act = ACT_END_SEGMENT;
                 } else {
-                    cnt.n_rej++;
-                    dt = dt / fmin(1.0 / qmin, q11 / gamma_c);
+                    double EEst = rms7(at);
+                    if (EEst <= 1.0) {
+                        cnt.n_acc++;
+                        // dt/q >= dt whenever q <= 1; at dt == dtmax the proposal is clipped back to dtmax, so the
+                        // two pow() are needed only when the step must shrink or has to grow back
+                        if (dt == O.dtmax && EEst <= eest_noshrink) {
+                            dtnew = dt;
+                        } else {
+                            double qq = 1.0 / qmax;
+                            if (EEst != 0.0) {
+                                qq = pow_nl(EEst, beta1) / pow_nl(qold, beta2);
+                                qq = fmax(1.0 / qmax, fmin(1.0 / qmin, qq / gamma_c));
+                            }
+                            dtnew = dt / qq;
+                        }
+                        qold = fmax(EEst, qoldinit);
+                        double ttmp = t + dt;
+                        if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
+                        hstep = ttmp - t;
+                        P_a = u[6]; dP_a = k[0][6];
+                        t = ttmp;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) { u[i] = tmp[i]; k[0][i] = k[S - 1][i]; }
+                        if (u[6] < 0.0) {  // positivity callback (reference src/solve.jl:78-83,159-160): re-evaluate f(u)
+                            u[6] = 0.0;
+                            tmp[6] = 0.0;
+                            phase = PH_CALLBACK;
+                        } else {
+                            act = ACT_AFTER_ACCEPT;
+                        }
+                    } else {
+                        cnt.n_rej++;
+                        double q11 = pow_nl(EEst, beta1);
+                        dt = dt / fmin(1.0 / qmin, q11 / gamma_c);
+                        act = ACT_BEGIN_STEP;
+                    }
                 }
             }
+        } else if (phase == PH_CALLBACK) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) k[0][i] = out[i];
+            act = ACT_AFTER_ACCEPT;
         }
-        // ---- termination tests at the segment end (reference src/solve.jl:174-176) and retirement
-        if (act) {
-            bool done = TORJ_FATAL(rstat) || seg >= O.n_segments || psi_cur > O.psi_stop || u[6] < O.p_stop;
-            if (done) {
-                a.B.status[ray] = rstat;
-                a.B.n_points[ray] = npts;
-                if (!TORJ_FATAL(rstat)) {
-                    a.B.P_final[ray] = u[6];
-                    a.B.P_dep[ray] = pdep;
-                    tot_dep += wgt * pdep;
-                    tot_w += wgt;
-                    rays_ok++;
+
+        // ---- transitions that need no RHS evaluation
+        while (act != ACT_NONE) {
+            if (act == ACT_AFTER_ACCEPT) {
+                put_point(t, u, u[6], -k[0][6]);  // dP/ds sample = P*alpha (reference src/solve.jl:171)
+                // streaming deposition over this step
+                double R = sqrt(u[0] * u[0] + u[1] * u[1]), psi_b, pR, pZ;
+                eval_psi(T, R, u[2], &psi_b, &pR, &pZ);
+                double dpsi_b = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
+                depo_step(dst, s_edges, n_psi, hstep, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, k[0][6], sink);
+                psi_cur = psi_b; dpsi_cur = dpsi_b;
+                dt = fmin(O.dtmax, dtnew);
+                act = ACT_BEGIN_STEP;
+            } else if (act == ACT_BEGIN_STEP) {
+                if (!(t < tstop)) { act = ACT_END_SEGMENT; continue; }
+                if (++nstep > O.max_steps) { rstat = 4; act = ACT_END_SEGMENT; continue; }  // TORJ_RAY_MAX_STEPS
+                dt = fmin(dt, tstop - t);
+                st = 1;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) tmp[i] = fma(dt * s_a[1][0], k[0][i], u[i]);
+                phase = PH_STAGE;
+                act = ACT_NONE;
+            } else if (act == ACT_END_SEGMENT) {
+                // termination tests at the segment end (reference src/solve.jl:174-176) and retirement
+                bool done = TORJ_FATAL(rstat) || seg >= O.n_segments || psi_cur > O.psi_stop || u[6] < O.p_stop;
+                if (done) {
+                    a.B.status[ray] = rstat;
+                    a.B.n_points[ray] = npts;
+                    if (!TORJ_FATAL(rstat)) {
+                        a.B.P_final[ray] = u[6];
+                        a.B.P_dep[ray] = pdep;
+                        tot_dep += wgt * pdep;
+                        tot_w += wgt;
+                        rays_ok++;
+                    }
+                    ray = -1;
+                    phase = PH_IDLE;
+                    act = ACT_NONE;
+                } else {
+                    act = ACT_BEGIN_SEGMENT;
                 }
-                ray = -1;
+            } else {  // ACT_BEGIN_SEGMENT: one fresh ODEProblem of the reference (src/solve.jl:155-161)
+                seg++;
+                t = (double)(seg - 1) * s_step + s0;
+                tstop = (double)seg * s_step + s0;
+                qold = qoldinit;
+                nstep = 0;
+                // first half of ode_determine_initdt; k[0] = f(u) is the FSAL derivative
+                double v0[7], v1[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    double sk = O.abstol + fabs(u[i]) * O.reltol;
+                    v0[i] = u[i] / sk; v1[i] = k[0][i] / sk;
+                }
+                double d0 = rms7(v0);
+                d1 = rms7(v1);
+                dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100.0;
+                dt0 = fmin(dt0, O.dtmax);
+                if (dt0 < 10.0 * 2.220446049250313e-16) {
+                    dt = 1e-6;
+                    act = ACT_BEGIN_STEP;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) tmp[i] = fma(dt0, k[0][i], u[i]);
+                    phase = PH_INITDT;
+                    act = ACT_NONE;
+                }
             }
         }
     }
