@@ -472,7 +472,10 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.J.first = b->traj_first; a.J.count = b->traj_count; a.J.max_pts = b->traj_max;
     a.J.s = b->d_ts; a.J.xyz = b->d_txyz; a.J.P = b->d_tP; a.J.dP = b->d_tdP; a.J.prof = b->d_tprof;
     a.n_psi = n_psi; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
-    size_t smem = 2 * (size_t)n_psi * sizeof(double);
+    size_t smem = (size_t)n_psi * sizeof(double);
+#if TORJ_K_SMEM
+    smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
+#endif
     int bps = 0;
     int64_t warps = (b->n + 31) / 32;
     int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);

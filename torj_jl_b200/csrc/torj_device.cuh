@@ -599,11 +599,11 @@ struct DepoState {
     double P_last;  // P at the last crossing
 };
 
-__device__ __forceinline__ int locate_shell(const double* g, int n, double psi) {  // upper_bound(psi) - 1
+__device__ __forceinline__ int locate_shell(const double* __restrict__ g, int n, double psi) {  // upper_bound(psi) - 1
     int lo = 0, hi = n;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (g[mid] <= psi) lo = mid + 1; else hi = mid;
+        if (__ldg(g + mid) <= psi) lo = mid + 1; else hi = mid;
     }
     return lo - 1;
 }
@@ -619,21 +619,21 @@ __device__ __forceinline__ double hermite_d(double f0, double f1, double d0, dou
 
 // Deposit callback: sink(shell, dP)
 template <class Sink>
-__device__ __forceinline__ void depo_step(DepoState& st, const double* g, int npsi, double h, double psi_a, double psi_b,
+__device__ __forceinline__ void depo_step(DepoState& st, const double* __restrict__ g, int npsi, double h, double psi_a, double psi_b,
                                           double dpsi_a, double dpsi_b, double P_a, double P_b, double dP_a, double dP_b,
                                           Sink&& sink) {
     while (true) {
         int lvl, nshell;
         if (psi_b < psi_a) {
             lvl = st.shell;
-            if (lvl < 0 || !(psi_b < g[lvl])) return;
+            if (lvl < 0 || !(psi_b < __ldg(g + lvl))) return;
             nshell = lvl - 1;
         } else {
             lvl = st.shell + 1;
-            if (lvl > npsi - 1 || !(psi_b >= g[lvl])) return;
+            if (lvl > npsi - 1 || !(psi_b >= __ldg(g + lvl))) return;
             nshell = lvl;
         }
-        double gl = g[lvl];
+        double gl = __ldg(g + lvl);
         double th = (gl - psi_a) / (psi_b - psi_a);
 #pragma unroll
         for (int it = 0; it < 3; ++it) {

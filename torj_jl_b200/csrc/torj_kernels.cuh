@@ -279,7 +279,12 @@ struct Scheme;
 template <> struct Scheme<0> { static constexpr int S = 7; static constexpr int ORDER = 5; };
 template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int ORDER = 3; };
 
+#ifndef TORJ_TPB
 #define TORJ_TPB 128
+#endif
+#ifndef TORJ_K_SMEM
+#define TORJ_K_SMEM 1  // 1: Runge-Kutta stage derivatives k[S][7] live in shared memory instead of (L1-backed) local memory
+#endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
@@ -297,13 +302,20 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
     extern __shared__ double smem[];
-    double* s_edges = smem;             // [n_psi]
-    double* s_bins = smem + a.n_psi;    // [n_psi]
+    double* s_bins = smem;                                 // [n_psi] block-local deposition bins
+    const double* __restrict__ s_edges = a.psi_edges;      // psi levels: read-only, through L1 (__ldg)
+#if TORJ_K_SMEM
+    double* ks = smem + a.n_psi + threadIdx.x;             // KK(j, i) at ks[(j*7+i)*TORJ_TPB]: conflict-free
+#define KK(j, i) ks[((j) * 7 + (i)) * TORJ_TPB]
+#else
+    double k_loc[S][7];
+#define KK(j, i) k_loc[j][i]
+#endif
     __shared__ unsigned long long s_cnt[7];
     __shared__ double s_tot[2];
     __shared__ double s_a[7][7], s_bt[7];
     const int n_psi = a.n_psi;
-    for (int j = threadIdx.x; j < n_psi; j += blockDim.x) { s_edges[j] = a.psi_edges[j]; s_bins[j] = 0.0; }
+    for (int j = threadIdx.x; j < n_psi; j += blockDim.x) s_bins[j] = 0.0;
     if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
     if (threadIdx.x < 49) s_a[threadIdx.x / 7][threadIdx.x % 7] = c_tab[SCH].a[threadIdx.x / 7][threadIdx.x % 7];
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     long long ray = -1;
     int phase = PH_IDLE, st = 0;
     bool exhausted = false;
-    double u[7], tmp[7], k[S][7];
+    double u[7], tmp[7];
     double s0 = 0.0, wgt = 0.0, pdep = 0.0;
     double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0, dt0 = 0.0, d1 = 0.0;
     double psi_cur = 0.0, dpsi_cur = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
         if (phase == PH_SEED) {
             // derivative at entry (FSAL seed), psi there, and the vacuum leg launch -> entry (P = 1, straight line)
 #pragma unroll
-            for (int i = 0; i < 7; ++i) k[0][i] = out[i];
+            for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
             double R = sqrt(u[0] * u[0] + u[1] * u[1]), pR, pZ;
             eval_psi(T, R, u[2], &psi_cur, &pR, &pZ);
             dpsi_cur = pR * (u[0] * out[0] + u[1] * out[1]) / R + pZ * out[2];
@@ -414,7 +426,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
             // second half of OrdinaryDiffEq's ode_determine_initdt (Hairer): out = f(u + dt0 f0)
             double v[7];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) v[i] = (out[i] - k[0][i]) / (O.abstol + fabs(u[i]) * O.reltol);
+            for (int i = 0; i < 7; ++i) v[i] = (out[i] - KK(0, i)) / (O.abstol + fabs(u[i]) * O.reltol);
             double d2 = rms7(v) / dt0;
             double md = fmax(d1, d2);
             // 10^(-(2 + log10 md)/order) = (100 md)^(-1/order)
@@ -423,13 +435,13 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
             act = ACT_BEGIN_STEP;
         } else if (phase == PH_STAGE) {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) k[st][i] = out[i];
+            for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
             if (st < S - 1) {
                 st++;
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
                     double acc = 0.0;
-                    for (int j = 0; j < st; ++j) acc = fma(s_a[st][j], k[j][i], acc);
+                    for (int j = 0; j < st; ++j) acc = fma(s_a[st][j], KK(j, i), acc);
                     tmp[i] = fma(dt, acc, u[i]);
                 }
             } else {
@@ -440,7 +452,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                 for (int i = 0; i < 7; ++i) {
                     double ut = 0.0;
 #pragma unroll
-                    for (int j = 0; j < S; ++j) ut = fma(s_bt[j], k[j][i], ut);
+                    for (int j = 0; j < S; ++j) ut = fma(s_bt[j], KK(j, i), ut);
                     ut *= dt;
                     at[i] = ut / (O.abstol + fmax(fabs(u[i]), fabs(tmp[i])) * O.reltol);
                     if (!(tmp[i] == tmp[i])) bad = true;
@@ -468,10 +480,10 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                         double ttmp = t + dt;
                         if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
                         hstep = ttmp - t;
-                        P_a = u[6]; dP_a = k[0][6];
+                        P_a = u[6]; dP_a = KK(0, 6);
                         t = ttmp;
 #pragma unroll
-                        for (int i = 0; i < 7; ++i) { u[i] = tmp[i]; k[0][i] = k[S - 1][i]; }
+                        for (int i = 0; i < 7; ++i) { u[i] = tmp[i]; KK(0, i) = KK(S - 1, i); }
                         if (u[6] < 0.0) {  // positivity callback (reference src/solve.jl:78-83,159-160): re-evaluate f(u)
                             u[6] = 0.0;
                             tmp[6] = 0.0;
@@ -489,19 +501,19 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
             }
         } else if (phase == PH_CALLBACK) {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) k[0][i] = out[i];
+            for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
             act = ACT_AFTER_ACCEPT;
         }
 
         // ---- transitions that need no RHS evaluation
         while (act != ACT_NONE) {
             if (act == ACT_AFTER_ACCEPT) {
-                put_point(t, u, u[6], -k[0][6]);  // dP/ds sample = P*alpha (reference src/solve.jl:171)
+                put_point(t, u, u[6], -KK(0, 6));  // dP/ds sample = P*alpha (reference src/solve.jl:171)
                 // streaming deposition over this step
                 double R = sqrt(u[0] * u[0] + u[1] * u[1]), psi_b, pR, pZ;
                 eval_psi(T, R, u[2], &psi_b, &pR, &pZ);
-                double dpsi_b = pR * (u[0] * k[0][0] + u[1] * k[0][1]) / R + pZ * k[0][2];
-                depo_step(dst, s_edges, n_psi, hstep, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, k[0][6], sink);
+                double dpsi_b = pR * (u[0] * KK(0, 0) + u[1] * KK(0, 1)) / R + pZ * KK(0, 2);
+                depo_step(dst, s_edges, n_psi, hstep, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, KK(0, 6), sink);
                 psi_cur = psi_b; dpsi_cur = dpsi_b;
                 dt = fmin(O.dtmax, dtnew);
                 act = ACT_BEGIN_STEP;
@@ -511,7 +523,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                 dt = fmin(dt, tstop - t);
                 st = 1;
 #pragma unroll
-                for (int i = 0; i < 7; ++i) tmp[i] = fma(dt * s_a[1][0], k[0][i], u[i]);
+                for (int i = 0; i < 7; ++i) tmp[i] = fma(dt * s_a[1][0], KK(0, i), u[i]);
                 phase = PH_STAGE;
                 act = ACT_NONE;
             } else if (act == ACT_END_SEGMENT) {
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
                     double sk = O.abstol + fabs(u[i]) * O.reltol;
-                    v0[i] = u[i] / sk; v1[i] = k[0][i] / sk;
+                    v0[i] = u[i] / sk; v1[i] = KK(0, i) / sk;
                 }
                 double d0 = rms7(v0);
                 d1 = rms7(v1);
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                     act = ACT_BEGIN_STEP;
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) tmp[i] = fma(dt0, k[0][i], u[i]);
+                    for (int i = 0; i < 7; ++i) tmp[i] = fma(dt0, KK(0, i), u[i]);
                     phase = PH_INITDT;
                     act = ACT_NONE;
                 }
@@ -583,6 +595,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
         if (s_bins[j] != 0.0) atomicAdd(&a.bins[j], s_bins[j]);
     if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
     if (threadIdx.x < 7) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
+#undef KK
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
