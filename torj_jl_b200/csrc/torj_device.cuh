@@ -24,6 +24,9 @@ namespace torj {
 #define TORJ_ME 9.1093837015e-31
 
 #define TORJ_MAX_GL 64
+#ifndef TORJ_ROW_FENCE
+#define TORJ_ROW_FENCE 1
+#endif
 #define TORJ_BESS_K 24
 
 struct DevTables {
@@ -173,6 +176,11 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             vZ[q] = fma(dwz[j], a[q], vZ[q]);
         }
         te = fma(wz[j], at, te);
+#if TORJ_ROW_FENCE
+        // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
+        // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
+        asm volatile("" ::: "memory");
+#endif
     }
     f.BR = v[0]; f.BR_R = vR[0]; f.BR_Z = vZ[0];
     f.BZ = v[1]; f.BZ_R = vR[1]; f.BZ_Z = vZ[1];
@@ -352,7 +360,8 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
 // k = rint(x log2 e), r = x - k ln2 (two-part), degree-13 Taylor polynomial on |r| <= ln2/2 (remainder < 4e-18),
 // scaled by 2^k built in the exponent field.
 __device__ __forceinline__ double exp_fast(double x) {
-    x = fmin(fmax(x, -708.0), 708.0);
+    x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
+    x = x > 708.0 ? 708.0 : x;
     const double kd = rint(x * 1.4426950408889634074);
     double r = fma(kd, -6.93147180369123816490e-01, x);
     r = fma(kd, -1.90821492927058770002e-10, r);
@@ -452,7 +461,9 @@ template <int M>
 __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt) {
     const double fm = (double)M, ifm = 1.0 / (double)M;
     const double A = fm * h.Y * h.ispar;  // m / m_0, m_0 = spar / Y
-    const double q = sqrt_fast(fmax(A * A - 1.0, 0.0));
+    double q2 = A * A - 1.0;
+    q2 = q2 > 0.0 ? q2 : 0.0;
+    const double q = sqrt_fast(q2);
     HarmCoef c;
     c.x_m = h.N_perp * h.iY * q;
     // gamma is linear in t on the resonance curve: gamma = (A + N_par q t)/spar  (== sqrt(1 + u_par^2 + u_perp^2))
@@ -475,7 +486,8 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
         const double xm = c.x_m;
         const double pmax = fabs(c.k1) + fabs(c.k2) * xm + fabs(c.k3m2) + fabs(c.k3) * xm * xm + fabs(c.k4) + fabs(c.k5)
                             + fabs(c.k6) * xm;
-        const double bound = 2.0 * pmax * fabs(c.scale) * exp_fast(fmin(0.0, c.e0 + fabs(c.e1)));
+        const double emax = c.e0 + fabs(c.e1);
+        const double bound = 2.0 * pmax * fabs(c.scale) * exp_fast(emax < 0.0 ? emax : 0.0);
         if (bound < h.floor_) { cnt.n_prune++; return 0.0; }
     }
     cnt.n_harm++;
@@ -496,7 +508,8 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     const double iNabs = rsqrt_fast(N2);
     const double ct = N_par * iNabs;
     const double ct2 = ct * ct;
-    const double st2 = fmax(0.0, (1.0 - ct) * (1.0 + ct));
+    double st2 = (1.0 - ct) * (1.0 + ct);
+    st2 = st2 > 0.0 ? st2 : 0.0;
     const double st = sqrt_fast(st2);                       // sin(acos(ct))
     h.N_perp = (N2 * iNabs) * st;                           // sqrt(N_abs^2 - N_par^2)
     h.N_par = N_par;

@@ -297,8 +297,14 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 enum { PH_IDLE = 0, PH_SEED = 1, PH_INITDT = 2, PH_STAGE = 3, PH_CALLBACK = 4 };
 enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT = 3, ACT_AFTER_ACCEPT = 4 };
 
+#ifdef TORJ_MAXNREG
+#define TORJ_TRACE_BOUNDS __maxnreg__(TORJ_MAXNREG)
+#else
+#define TORJ_TRACE_BOUNDS __launch_bounds__(TORJ_TPB, TORJ_MINB)
+#endif
+
 template <int SCH>
-__global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
+__global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
     extern __shared__ double smem[];
@@ -329,8 +335,8 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     const unsigned FULL = 0xffffffffu;
     const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
-    // EEst below this always gives q <= 1 (qold >= qoldinit): (gamma*qoldinit^beta2)^(1/beta1)
-    const double eest_noshrink = pow(gamma_c * pow(qoldinit, beta2), 1.0 / beta1);
+    // q = EEst^beta1 / qold^beta2 / gamma <= 1  <=>  EEst^7 <= gamma^(10 k) qold^4   (beta1 = 7/(10k), beta2 = 4/(10k))
+    const double gamma_pow = pow(gamma_c, 10.0 * ORDER);
     const double s_step = O.s_max / (double)O.n_segments;
 
     // per-lane ray state
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     double s0 = 0.0, wgt = 0.0, pdep = 0.0;
     double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0, dt0 = 0.0, d1 = 0.0;
     double psi_cur = 0.0, dpsi_cur = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
-    int seg = 0, npts = 0, rstat = 0, nstep = 0;
+    int seg = 0, npts = 0, rstat = 0, nstep = 0, last_stat = 0;
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
     Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -350,6 +356,10 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
     long long tj = -1;  // index into the trajectory window or -1
 #pragma unroll
     for (int i = 0; i < 7; ++i) { u[i] = 0.0; tmp[i] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < S; ++j)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) KK(j, i) = 0.0;
 
     auto sink = [&](int shell, double dP) {
         atomicAdd(&s_bins[shell], wgt * dP);
@@ -392,6 +402,13 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                     int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
                     rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
                     seg = 0; npts = 0; rstat = 0; pdep = 0.0;
+                    if (TORJ_FATAL(last_stat)) {  // a dead ray may have left NaN/Inf in the stage slots (0 * NaN != 0)
+#pragma unroll
+                        for (int j = 0; j < S; ++j)
+#pragma unroll
+                            for (int i = 0; i < 7; ++i) KK(j, i) = 0.0;
+                        last_stat = 0;
+                    }
                     tj = (idx >= a.J.first && idx < a.J.first + a.J.count) ? idx - a.J.first : -1;
                     // samples 1 and 2: launch point and plasma entry (reference src/solve.jl:149-153)
                     double xl[3] = {a.B.pos[idx], a.B.pos[n + idx], a.B.pos[2 * n + idx]};
@@ -438,12 +455,17 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
             for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
             if (st < S - 1) {
                 st++;
+                // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
+                // stale slots hold finite values of the previous step, so the trip count is lane-independent
+                double acc[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    double acc = 0.0;
-                    for (int j = 0; j < st; ++j) acc = fma(s_a[st][j], KK(j, i), acc);
-                    tmp[i] = fma(dt, acc, u[i]);
+                for (int j = 0; j < S - 1; ++j) {
+                    const double aj = s_a[st][j];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) acc[i] = fma(aj, KK(j, i), acc[i]);
                 }
+#pragma unroll
+                for (int i = 0; i < 7; ++i) tmp[i] = fma(dt, acc[i], u[i]);
             } else {
                 // tmp is the proposed new state (FSAL); embedded error estimate and PI controller
                 double at[7];
@@ -454,7 +476,8 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
 #pragma unroll
                     for (int j = 0; j < S; ++j) ut = fma(s_bt[j], KK(j, i), ut);
                     ut *= dt;
-                    at[i] = ut / (O.abstol + fmax(fabs(u[i]), fabs(tmp[i])) * O.reltol);
+                    const double au = fabs(u[i]), an = fabs(tmp[i]);
+                    at[i] = ut * rcp_fast(O.abstol + (au > an ? au : an) * O.reltol);
                     if (!(tmp[i] == tmp[i])) bad = true;
                 }
                 if (bad) {
@@ -466,7 +489,8 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                         cnt.n_acc++;
                         // dt/q >= dt whenever q <= 1; at dt == dtmax the proposal is clipped back to dtmax, so the
                         // two pow() are needed only when the step must shrink or has to grow back
-                        if (dt == O.dtmax && EEst <= eest_noshrink) {
+                        const double e2 = EEst * EEst, q2 = qold * qold;
+                        if (dt == O.dtmax && e2 * e2 * e2 * EEst <= gamma_pow * (q2 * q2)) {
                             dtnew = dt;
                         } else {
                             double qq = 1.0 / qmax;
@@ -532,6 +556,7 @@ __global__ void __launch_bounds__(TORJ_TPB, TORJ_MINB) k_trace(TraceArgs a) {
                 if (done) {
                     a.B.status[ray] = rstat;
                     a.B.n_points[ray] = npts;
+                    last_stat = rstat;
                     if (!TORJ_FATAL(rstat)) {
                         a.B.P_final[ray] = u[6];
                         a.B.P_dep[ray] = pdep;
