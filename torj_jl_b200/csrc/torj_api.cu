@@ -37,10 +37,14 @@ struct torj_ctx {
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the last k_trace launch
     bool ev_valid = false;
+    struct torj_bundle* ws = nullptr;  // workspace of the one-shot torj_trace call, kept between calls
 };
+
+static uint64_t g_plasma_serial = 0;
 
 struct torj_plasma {
     torj_ctx* ctx = nullptr;
+    uint64_t id = 0;  // unique per created plasma (addresses can be recycled)
     DevTables T{};
     double2* dA = nullptr;
     double2* dB = nullptr;
@@ -69,6 +73,9 @@ struct torj_bundle {
     int traj_max = 0;
     double *d_ts = nullptr, *d_txyz = nullptr, *d_tP = nullptr, *d_tdP = nullptr, *d_tprof = nullptr;
     int traj_prof_npsi = 0;
+    // what the device copies of psi_edges / dV were computed from (skips the re-upload when unchanged)
+    std::vector<double> h_edges;
+    uint64_t edges_plasma = 0;
 };
 
 static int set_device(const torj_ctx* c) {
@@ -158,6 +165,7 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
 void torj_ctx_destroy(torj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->ws) torj_bundle_destroy(c->ws);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -249,6 +257,7 @@ int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, 
     if (set_device(c)) return 1;
     torj_plasma* p = new torj_plasma();
     p->ctx = c;
+    p->id = ++g_plasma_serial;
     size_t nodes = (size_t)(g->nR + 2) * (g->nZ + 2);
     std::vector<double2> hA(2 * nodes), hB(nodes);
     for (size_t k = 0; k < nodes; ++k) {
@@ -361,6 +370,20 @@ static void free_traj(torj_bundle* b) {
     b->traj_prof_npsi = 0;
 }
 
+static int bundle_upload(torj_bundle* b, const double* pos, const double* dir, const double* weight,
+                         const double* freq_hz, const int32_t* mode) {
+    torj_ctx* c = b->ctx;
+    const int64_t n = b->n;
+    size_t nf = b->per_ray_fm ? (size_t)n : 1;
+    CK(cudaMemcpyAsync(b->d_pos, pos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_dir, dir, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_w, weight, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_freq, freq_hz, nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b->d_mode, mode, nf * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // host buffers may be released by the caller on return
+    return 0;
+}
+
 int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* dir, const double* weight,
                        const double* freq_hz, const int32_t* mode, int32_t per_ray_fm, torj_bundle** out) {
     if (!c || !out || n < 1) FAIL("torj_bundle_create: bad argument");
@@ -382,16 +405,11 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
     CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_counters, 7 * sizeof(unsigned long long)));
-    CK(cudaMemcpyAsync(b->d_pos, pos, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(b->d_dir, dir, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(b->d_w, weight, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(b->d_freq, freq_hz, nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(b->d_mode, mode, nf * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));  // host buffers may be released by the caller on return
     BundleDev& B = b->B;
     B.n_rays = n; B.pos = b->d_pos; B.dir = b->d_dir; B.weight = b->d_w; B.freq = b->d_freq; B.mode = b->d_mode;
     B.per_ray_fm = per_ray_fm; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
     B.P_final = b->d_Pf; B.P_dep = b->d_Pdep; B.n_points = b->d_npts;
+    if (bundle_upload(b, pos, dir, weight, freq_hz, mode)) return 1;
     *out = b;
     return 0;
 }
@@ -452,11 +470,16 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         CK(cudaMalloc(&b->d_tprof, (size_t)b->traj_count * n_psi * sizeof(double)));
         b->traj_prof_npsi = n_psi;
     }
-    std::vector<double> dV(n_psi, 1.0);
-    for (int j = 0; j + 1 < n_psi; ++j) dV[j] = volume_at(p, psi_edges[j + 1]) - volume_at(p, psi_edges[j]);
-    CK(cudaMemcpyAsync(b->d_edges, psi_edges, n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->d_dV, dV.data(), n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // dV is a local; psi_edges belongs to the caller
+    if (b->edges_plasma != p->id || (int)b->h_edges.size() != n_psi ||
+        memcmp(b->h_edges.data(), psi_edges, n_psi * sizeof(double)) != 0) {
+        std::vector<double> dV(n_psi, 1.0);
+        for (int j = 0; j + 1 < n_psi; ++j) dV[j] = volume_at(p, psi_edges[j + 1]) - volume_at(p, psi_edges[j]);
+        CK(cudaMemcpyAsync(b->d_edges, psi_edges, n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_dV, dV.data(), n_psi * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // dV is a local; psi_edges belongs to the caller
+        b->h_edges.assign(psi_edges, psi_edges + n_psi);
+        b->edges_plasma = p->id;
+    }
     CK(cudaMemsetAsync(b->d_bins, 0, (n_psi + 2) * sizeof(double), st));
     CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(b->d_counters, 0, 7 * sizeof(unsigned long long), st));
@@ -559,14 +582,32 @@ int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
                double* P_final, double* P_dep, int32_t* n_points, int32_t* status, int64_t traj_first, int64_t traj_count,
                int32_t traj_max_pts, double* traj_s, double* traj_xyz, double* traj_P, double* traj_dP_ds,
                double* traj_dP_dV_ray, torj_counters* counters) {
-    torj_bundle* b = nullptr;
-    int rc = torj_bundle_create(c, n_rays, pos, dir, weight, freq_hz, mode, per_ray_fm, &b);
-    if (rc) return rc;
-    if (traj_count > 0) rc = torj_bundle_set_window(b, traj_first, traj_count, traj_max_pts);
+    // the device workspace of the previous call is reused when the bundle shape is unchanged (no cudaMalloc/cudaFree
+    // on the repeated-call path of make_beam scans)
+    int rc = 0;
+    torj_bundle* b = c->ws;
+    if (b && (b->n != n_rays || b->per_ray_fm != per_ray_fm)) {
+        torj_bundle_destroy(b);
+        b = c->ws = nullptr;
+    }
+    if (!b) {
+        rc = torj_bundle_create(c, n_rays, pos, dir, weight, freq_hz, mode, per_ray_fm, &b);
+        if (rc) return rc;
+        c->ws = b;
+    } else {
+        if (set_device(c)) return 1;
+        rc = bundle_upload(b, pos, dir, weight, freq_hz, mode);
+        if (rc) return rc;
+    }
+    if (traj_count != b->traj_count || traj_first != b->traj_first || (traj_count > 0 && traj_max_pts != b->traj_max))
+        rc = torj_bundle_set_window(b, traj_first, traj_count, traj_max_pts);
     if (!rc) rc = torj_bundle_trace(b, p, opt, s_max, n_psi, psi_edges);
     if (!rc) rc = torj_bundle_results(b, dP_dV, deposited_power, P_final, P_dep, n_points, status, counters);
     if (!rc && traj_count > 0) rc = torj_bundle_trajectories(b, traj_s, traj_xyz, traj_P, traj_dP_ds, traj_dP_dV_ray);
-    torj_bundle_destroy(b);
+    if (rc) {  // do not keep a workspace in an unknown state
+        torj_bundle_destroy(b);
+        c->ws = nullptr;
+    }
     return rc;
 }
 

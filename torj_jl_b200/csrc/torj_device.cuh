@@ -142,22 +142,24 @@ struct Fields {  // value, d/dR, d/dZ
     double Bp, Bp_R, Bp_Z;
     double L, L_R, L_Z;  // ln n_e
     double lnTe;
+    double psi, psi_R, psi_Z;  // psi_N rides along: its coefficients share the (ln T_e, psi_N) loads
 };
 
-// all five RHS fields at a point inside the grid
+// all five RHS fields (and optionally psi_N) at a point inside the grid
+template <bool WITH_PSI>
 __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f) {
     double wr[4], dwr[4], wz[4], dwz[4];
     int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
     int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
     double v[4] = {0, 0, 0, 0}, vR[4] = {0, 0, 0, 0}, vZ[4] = {0, 0, 0, 0};
-    double te = 0.0;
+    double te = 0.0, ps = 0.0, psR = 0.0, psZ = 0.0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         size_t node = (size_t)(bz + j) * T.row + br;
         const double2* pa = T.A + 2 * node;
         const double2* pb = T.B + node;
         double a[4] = {0, 0, 0, 0}, aR[4] = {0, 0, 0, 0};
-        double at = 0.0;
+        double at = 0.0, ap = 0.0, apR = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             double2 q0 = __ldg(pa + 2 * i);
@@ -168,6 +170,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             a[2] = fma(wr[i], q1.x, a[2]); aR[2] = fma(dwr[i], q1.x, aR[2]);
             a[3] = fma(wr[i], q1.y, a[3]); aR[3] = fma(dwr[i], q1.y, aR[3]);
             at = fma(wr[i], q2.x, at);
+            if (WITH_PSI) { ap = fma(wr[i], q2.y, ap); apR = fma(dwr[i], q2.y, apR); }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -176,6 +179,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             vZ[q] = fma(dwz[j], a[q], vZ[q]);
         }
         te = fma(wz[j], at, te);
+        if (WITH_PSI) { ps = fma(wz[j], ap, ps); psR = fma(wz[j], apR, psR); psZ = fma(dwz[j], ap, psZ); }
 #if TORJ_ROW_FENCE
         // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
         // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
@@ -187,6 +191,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
     f.Bp = v[2]; f.Bp_R = vR[2]; f.Bp_Z = vZ[2];
     f.L = v[3]; f.L_R = vR[3]; f.L_Z = vZ[3];
     f.lnTe = te;
+    f.psi = ps; f.psi_R = psR; f.psi_Z = psZ;
 }
 
 // one field (0..3 from tabA, 4 = lnTe, 5 = psi) with value, gradient and mixed derivative, any position:
@@ -226,9 +231,10 @@ __device__ __forceinline__ bool inside_grid(const DevTables& T, double R, double
     return R >= T.r0 && R <= T.rlast && Z >= T.z0 && Z <= T.zlast;
 }
 
+template <bool WITH_PSI>
 __device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f) {
     if (inside_grid(T, R, Z)) {
-        eval_fields_in(T, R, Z, f);
+        eval_fields_in<WITH_PSI>(T, R, Z, f);
     } else {
         double d0, d1;
         eval_field_ext(T, 0, R, Z, &f.BR, &f.BR_R, &f.BR_Z);
@@ -236,6 +242,8 @@ __device__ __forceinline__ void eval_fields(const DevTables& T, double R, double
         eval_field_ext(T, 2, R, Z, &f.Bp, &f.Bp_R, &f.Bp_Z);
         eval_field_ext(T, 3, R, Z, &f.L, &f.L_R, &f.L_Z);
         eval_field_ext(T, 4, R, Z, &f.lnTe, &d0, &d1);
+        f.psi = f.psi_R = f.psi_Z = 0.0;
+        if (WITH_PSI) eval_field_ext(T, 5, R, Z, &f.psi, &f.psi_R, &f.psi_Z);
     }
 }
 
@@ -549,7 +557,8 @@ struct PointVals {
     double X, Y, N_par, b[3], Te, Lambda;
 };
 
-template <bool WITH_ALPHA>
+// WITH_PSI: du[7] = psi_N at the point and du[8] = grad(psi_N) . dx/ds (inputs of the streaming deposition)
+template <bool WITH_ALPHA, bool WITH_PSI = false>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
                                     PointVals* pv = nullptr) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
@@ -558,7 +567,7 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
     const double R = R2 * iR;
     const double c = x * iR, s = y * iR;
     Fields f;
-    eval_fields(T, R, z, f);
+    eval_fields<WITH_PSI>(T, R, z, f);
     const double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
     const double iB = rsqrt_fast(B2);
     const double Babs = B2 * iB;
@@ -588,6 +597,10 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
     const double inorm = rsqrt_fast(hx * hx + hy * hy + hz * hz);
     du[0] = hx * inorm; du[1] = hy * inorm; du[2] = hz * inorm;
     du[3] = -gx * inorm; du[4] = -gy * inorm; du[5] = -gz * inorm;
+    if (WITH_PSI) {
+        du[7] = f.psi;
+        du[8] = f.psi_R * (c * du[0] + s * du[1]) + f.psi_Z * du[2];
+    }
     const double N2 = Nx * Nx + Ny * Ny + Nz * Nz;
     if (WITH_ALPHA) {
         const double alpha = abs_albajar(rc, X, Y, iY, N2, Np, f.lnTe, cnt);

@@ -285,6 +285,12 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_K_SMEM
 #define TORJ_K_SMEM 1  // 1: Runge-Kutta stage derivatives k[S][7] live in shared memory instead of (L1-backed) local memory
 #endif
+#ifndef TORJ_PSI_IN_RHS
+#define TORJ_PSI_IN_RHS 1  // 1: every RHS evaluation also returns psi_N and its arc-length derivative (no extra loads)
+#endif
+#ifndef TORJ_ERR_INCR
+#define TORJ_ERR_INCR 0  // 1: accumulate the embedded error estimate stage by stage (7 more live registers per lane)
+#endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
@@ -346,7 +352,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     double u[7], tmp[7];
     double s0 = 0.0, wgt = 0.0, pdep = 0.0;
     double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0, dt0 = 0.0, d1 = 0.0;
-    double psi_cur = 0.0, dpsi_cur = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
+    double psi_cur = 0.0, dpsi_cur = 0.0, psi_new = 0.0, dpsi_new = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
+#if TORJ_ERR_INCR
+    double err[7] = {0, 0, 0, 0, 0, 0, 0};
+#endif
     int seg = 0, npts = 0, rstat = 0, nstep = 0, last_stat = 0;
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
@@ -421,8 +430,16 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         if (__all_sync(FULL, phase == PH_IDLE && exhausted)) break;
 
         // ---- the one RHS evaluation of this trip (reference src/solve.jl:85-95), warp-converged
-        double out[7];
-        if (phase != PH_IDLE) rhs<true>(T, rc, tmp, out, cnt);
+        double out[9];
+        if (phase != PH_IDLE) rhs<true, TORJ_PSI_IN_RHS != 0>(T, rc, tmp, out, cnt);
+#if !TORJ_PSI_IN_RHS
+        auto psi_here = [&](const double* xx, const double* dir) {  // psi_N and grad(psi_N).dx/ds at xx
+            double R = sqrt(xx[0] * xx[0] + xx[1] * xx[1]), pR, pZ;
+            eval_psi(T, R, xx[2], &out[7], &pR, &pZ);
+            out[8] = pR * (xx[0] * dir[0] + xx[1] * dir[1]) / R + pZ * dir[2];
+        };
+        if (phase == PH_SEED || phase == PH_CALLBACK || (phase == PH_STAGE && st == S - 1)) psi_here(tmp, out);
+#endif
 
         // ---- phase bookkeeping
         int act = ACT_NONE;
@@ -430,9 +447,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             // derivative at entry (FSAL seed), psi there, and the vacuum leg launch -> entry (P = 1, straight line)
 #pragma unroll
             for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
-            double R = sqrt(u[0] * u[0] + u[1] * u[1]), pR, pZ;
-            eval_psi(T, R, u[2], &psi_cur, &pR, &pZ);
-            dpsi_cur = pR * (u[0] * out[0] + u[1] * out[1]) / R + pZ * out[2];
+            psi_cur = out[7];
+            dpsi_cur = out[8];
             double psl = a.B.psi_launch[ray];
             dst.shell = locate_shell(s_edges, n_psi, psl);
             dst.valid = 0; dst.P_last = 1.0;
@@ -451,8 +467,16 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
             act = ACT_BEGIN_STEP;
         } else if (phase == PH_STAGE) {
+            {
+                const double bj = s_bt[st];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
+                for (int i = 0; i < 7; ++i) {
+                    KK(st, i) = out[i];
+#if TORJ_ERR_INCR
+                    err[i] = fma(bj, out[i], err[i]);
+#endif
+                }
+            }
             if (st < S - 1) {
                 st++;
                 // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
@@ -467,15 +491,22 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) tmp[i] = fma(dt, acc[i], u[i]);
             } else {
-                // tmp is the proposed new state (FSAL); embedded error estimate and PI controller
+                // tmp is the proposed new state (FSAL); embedded error estimate (err = sum_j btilde_j k_j, accumulated
+                // stage by stage) and PI controller
+                psi_new = out[7];
+                dpsi_new = out[8];
                 double at[7];
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
+#if TORJ_ERR_INCR
+                    const double ut = err[i] * dt;
+#else
                     double ut = 0.0;
 #pragma unroll
                     for (int j = 0; j < S; ++j) ut = fma(s_bt[j], KK(j, i), ut);
                     ut *= dt;
+#endif
                     const double au = fabs(u[i]), an = fabs(tmp[i]);
                     at[i] = ut * rcp_fast(O.abstol + (au > an ? au : an) * O.reltol);
                     if (!(tmp[i] == tmp[i])) bad = true;
@@ -526,6 +557,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         } else if (phase == PH_CALLBACK) {
 #pragma unroll
             for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
+            psi_new = out[7];
+            dpsi_new = out[8];
             act = ACT_AFTER_ACCEPT;
         }
 
@@ -533,12 +566,9 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         while (act != ACT_NONE) {
             if (act == ACT_AFTER_ACCEPT) {
                 put_point(t, u, u[6], -KK(0, 6));  // dP/ds sample = P*alpha (reference src/solve.jl:171)
-                // streaming deposition over this step
-                double R = sqrt(u[0] * u[0] + u[1] * u[1]), psi_b, pR, pZ;
-                eval_psi(T, R, u[2], &psi_b, &pR, &pZ);
-                double dpsi_b = pR * (u[0] * KK(0, 0) + u[1] * KK(0, 1)) / R + pZ * KK(0, 2);
-                depo_step(dst, s_edges, n_psi, hstep, psi_cur, psi_b, dpsi_cur, dpsi_b, P_a, u[6], dP_a, KK(0, 6), sink);
-                psi_cur = psi_b; dpsi_cur = dpsi_b;
+                // streaming deposition over this step (psi and its arc-length derivative came with the FSAL stage)
+                depo_step(dst, s_edges, n_psi, hstep, psi_cur, psi_new, dpsi_cur, dpsi_new, P_a, u[6], dP_a, KK(0, 6), sink);
+                psi_cur = psi_new; dpsi_cur = dpsi_new;
                 dt = fmin(O.dtmax, dtnew);
                 act = ACT_BEGIN_STEP;
             } else if (act == ACT_BEGIN_STEP) {
@@ -546,8 +576,17 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 if (++nstep > O.max_steps) { rstat = 4; act = ACT_END_SEGMENT; continue; }  // TORJ_RAY_MAX_STEPS
                 dt = fmin(dt, tstop - t);
                 st = 1;
+                {
+                    const double a10 = dt * s_a[1][0], b0 = s_bt[0];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) tmp[i] = fma(dt * s_a[1][0], KK(0, i), u[i]);
+                    for (int i = 0; i < 7; ++i) {
+                        const double k0 = KK(0, i);
+                        tmp[i] = fma(a10, k0, u[i]);
+#if TORJ_ERR_INCR
+                        err[i] = b0 * k0;
+#endif
+                    }
+                }
                 phase = PH_STAGE;
                 act = ACT_NONE;
             } else if (act == ACT_END_SEGMENT) {
