@@ -80,7 +80,7 @@ def cpu_baseline(rank_bundle, seconds_target=15.0):
     """Oracle port on all host cores over a bounded sample of the same bundle (rays spread evenly over it)."""
     import torj_jl_b200 as tj
     from oracle import torj_oracle as O
-    cores = O.max_threads()
+    cores = len(os.sched_getaffinity(0))  # torchrun exports OMP_NUM_THREADS=1; the oracle is told the count explicitly
     arr = tj.solovev_arrays(257, 257)
     opl = O.OraclePlasma(*arr.values())
     gl = np.polynomial.legendre.leggauss(WORKLOAD["n_gl"])
@@ -257,7 +257,7 @@ def main():
                 "e2e": {"value": steps_all / (e2e_ms * 1e-3), "unit": "ray-steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "rays_per_s": rays_all / (e2e_ms * 1e-3)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-                "absorbed_fraction": dep.value}
+                "absorbed_fraction": dep.value / max(1, world) if world > 1 else dep.value}
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline((pos, dirs, w)).items() if k in ("value", "unit", "cores", "kind", "sample", "rays_per_s")}
         print(json.dumps(line), flush=True)
