@@ -67,6 +67,7 @@ typedef struct torj_counters {
     int64_t n_harm;  /* harmonic integrals evaluated (src/absorption.jl:217) */
     int64_t n_rays_ok;
     int64_t n_harm_pruned; /* harmonic integrals skipped by the alpha_floor bound */
+    int64_t n_alpha_skipped; /* inner Runge-Kutta stages that took alpha = 0 on the 1e10-margin rule (alpha_floor > 0 only) */
 } torj_counters;
 
 typedef struct torj_grid {

@@ -177,8 +177,10 @@ def test_alpha_floor_pruning_is_invisible_at_tolerance(gpu_full, launcher):
     pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
     a = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI)
     b = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=EXACT())
-    assert a["counters"]["n_harm_pruned"] > 0 and b["counters"]["n_harm_pruned"] == 0
-    assert a["counters"]["n_harm"] + a["counters"]["n_harm_pruned"] == b["counters"]["n_harm"]
+    ca, cb = a["counters"], b["counters"]
+    assert ca["n_harm_pruned"] > 0 and ca["n_alpha_skipped"] > 0 and cb["n_harm_pruned"] == 0 and cb["n_alpha_skipped"] == 0
+    assert ca["n_alpha"] + ca["n_alpha_skipped"] == cb["n_alpha"] == cb["n_rhs"] == ca["n_rhs"]
+    assert ca["n_harm"] < cb["n_harm"]
     assert np.array_equal(a["n_points"], b["n_points"])
     assert np.abs(a["P_final"] - b["P_final"]).max() < 1e-13
     assert abs(a["deposited_power"] - b["deposited_power"]) < 1e-12

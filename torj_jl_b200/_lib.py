@@ -23,7 +23,7 @@ class TorjOptions(C.Structure):
 
 class TorjCounters(C.Structure):
     _fields_ = [("n_acc", C.c_int64), ("n_rej", C.c_int64), ("n_rhs", C.c_int64), ("n_alpha", C.c_int64),
-                ("n_harm", C.c_int64), ("n_rays_ok", C.c_int64), ("n_harm_pruned", C.c_int64)]
+                ("n_harm", C.c_int64), ("n_rays_ok", C.c_int64), ("n_harm_pruned", C.c_int64), ("n_alpha_skipped", C.c_int64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -404,7 +404,7 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     CK(cudaMalloc(&b->d_status, n * sizeof(int)));
     CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
     CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
-    CK(cudaMalloc(&b->d_counters, 7 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long)));
     BundleDev& B = b->B;
     B.n_rays = n; B.pos = b->d_pos; B.dir = b->d_dir; B.weight = b->d_w; B.freq = b->d_freq; B.mode = b->d_mode;
     B.per_ray_fm = per_ray_fm; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
@@ -482,7 +482,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     }
     CK(cudaMemsetAsync(b->d_bins, 0, (n_psi + 2) * sizeof(double), st));
     CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
-    CK(cudaMemsetAsync(b->d_counters, 0, 7 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), st));
     if (b->traj_count > 0) CK(cudaMemsetAsync(b->d_tprof, 0, (size_t)b->traj_count * n_psi * sizeof(double), st));
 
     SolverOpts so = to_sopts(&od, s_max);
@@ -538,7 +538,7 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
     if (P_dep) CK(cudaMemcpyAsync(P_dep, b->d_Pdep, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (n_points) CK(cudaMemcpyAsync(n_points, b->d_npts, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (status) CK(cudaMemcpyAsync(status, b->d_status, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    unsigned long long cn[7];
+    unsigned long long cn[8];
     CK(cudaMemcpyAsync(cn, b->d_counters, sizeof cn, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (dP_dV) memcpy(dP_dV, prof.data(), b->n_psi * sizeof(double));
@@ -547,6 +547,7 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
         counters->n_acc = (int64_t)cn[0]; counters->n_rej = (int64_t)cn[1]; counters->n_rhs = (int64_t)cn[2];
         counters->n_alpha = (int64_t)cn[3]; counters->n_harm = (int64_t)cn[4]; counters->n_rays_ok = (int64_t)cn[5];
         counters->n_harm_pruned = (int64_t)cn[6];
+        counters->n_alpha_skipped = (int64_t)cn[7];
     }
     return 0;
 }

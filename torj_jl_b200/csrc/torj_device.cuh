@@ -80,7 +80,7 @@ __device__ __forceinline__ RayConst make_ray_const(double f, int mode, double te
 }
 
 struct Counters {
-    unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm, n_prune;
+    unsigned int n_acc, n_rej, n_rhs, n_alpha, n_harm, n_prune, n_askip;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -465,8 +465,10 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef& c) {
 // Series length: |term_K| = y^K M!/(K!(M+K)!) (x (M+2K) for D) with y = x_m^2/4: K=12 leaves < 5e-14 for
 // x_m <= 3.2 (m=2 layer: x_m ~ 1; m=3 next to it: x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
 // One sqrt per harmonic; everything else is products of the reciprocals prepared in abs_albajar.
+// `safe` is cleared unless the bound is below floor * TORJ_SKIP_MARGIN (see abs_albajar).
+#define TORJ_SKIP_MARGIN 1e-10
 template <int M>
-__device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt) {
+__device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe) {
     const double fm = (double)M, ifm = 1.0 / (double)M;
     const double A = fm * h.Y * h.ispar;  // m / m_0, m_0 = spar / Y
     double q2 = A * A - 1.0;
@@ -496,8 +498,13 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
                             + fabs(c.k6) * xm;
         const double emax = c.e0 + fabs(c.e1);
         const double bound = 2.0 * pmax * fabs(c.scale) * exp_fast(emax < 0.0 ? emax : 0.0);
-        if (bound < h.floor_) { cnt.n_prune++; return 0.0; }
+        if (bound < h.floor_) {
+            cnt.n_prune++;
+            if (!(bound < h.floor_ * TORJ_SKIP_MARGIN)) safe = false;
+            return 0.0;
+        }
     }
+    safe = false;
     cnt.n_harm++;
     if (c.x_m <= 3.2) return harmonic_sum<M, 12, false>(c);
     return harmonic_sum_large<M>(c);
@@ -505,8 +512,13 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
 
 // reference src/absorption.jl:191-226 (+ the T_e evaluation of :233). omega enters only through omega/c.
 // N2 = |N|^2, iY = 1/Y, lnTe = spline value (T_e = exp(lnTe), reference src/plasma.jl:87-89).
+// skip_ok (out): true when every harmonic is either pruned with a 1e10 margin below alpha_floor or more than 2 % away
+// (in m_0) from becoming eligible. The integrator then takes alpha = 0 at the inner Runge-Kutta stages of the NEXT
+// step, which lie within dtmax (0.1 mm) of this point: the bound would have to grow by 1e10 (its exponent by 23)
+// and m_0 = sqrt(1-N_par^2)/Y to move by 2 % over a distance far below the cell size of the spline tables.
 __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double iY, double N2, double N_par,
-                                              double lnTe, Counters& cnt) {
+                                              double lnTe, Counters& cnt, bool& skip_ok) {
+    skip_ok = false;
     if (lnTe < rc.ln_te_min) return 0.0;  // Te < te_min
     cnt.n_alpha++;
     HarmPre h;
@@ -544,8 +556,16 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     h.to_alpha = 2.0 * M_PI * M_PI * X * rc.w_over_c * h.ispar;
     h.floor_ = rc.alpha_floor;
     double alpha = 0.0;
-    if (2.0 >= m_0 && rc.max_harmonic >= 2) alpha += harmonic_alpha<2>(h, cnt);
-    if (3.0 >= m_0 && rc.max_harmonic >= 3) alpha += harmonic_alpha<3>(h, cnt);
+    bool safe = rc.alpha_floor > 0.0;
+    if (rc.max_harmonic >= 2) {
+        if (2.0 >= m_0) alpha += harmonic_alpha<2>(h, cnt, safe);
+        else if (!(m_0 - 2.0 > 0.02 * m_0)) safe = false;
+    }
+    if (rc.max_harmonic >= 3) {
+        if (3.0 >= m_0) alpha += harmonic_alpha<3>(h, cnt, safe);
+        else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
+    }
+    skip_ok = safe;
     return alpha;
 }
 
@@ -558,9 +578,11 @@ struct PointVals {
 };
 
 // WITH_PSI: du[7] = psi_N at the point and du[8] = grad(psi_N) . dx/ds (inputs of the streaming deposition)
+// alpha_skip (in/out, optional): on entry true = take alpha = 0 without evaluating it (see abs_albajar); on exit, when
+// alpha was evaluated, whether the next step's inner stages may skip it.
 template <bool WITH_ALPHA, bool WITH_PSI = false>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
-                                    PointVals* pv = nullptr) {
+                                    PointVals* pv = nullptr, bool skip_alpha = false, bool* skip_ok = nullptr) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
     const double R2 = fma(x, x, y * y);
     const double iR = rsqrt_fast(R2);
@@ -603,8 +625,15 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
     }
     const double N2 = Nx * Nx + Ny * Ny + Nz * Nz;
     if (WITH_ALPHA) {
-        const double alpha = abs_albajar(rc, X, Y, iY, N2, Np, f.lnTe, cnt);
-        du[6] = -u[6] * alpha;
+        if (skip_alpha) {
+            du[6] = 0.0;
+            cnt.n_askip++;
+        } else {
+            bool ok;
+            const double alpha = abs_albajar(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
+            du[6] = -u[6] * alpha;
+            if (skip_ok) *skip_ok = ok;
+        }
     } else {
         du[6] = 0.0;
     }

@@ -191,7 +191,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
     double Np[3];
     {
         double u[7] = {p[0], p[1], p[2], N0[0], N0[1], N0[2], 1.0}, du[7];
-        Counters c0 = {0, 0, 0, 0, 0, 0};
+        Counters c0 = {0, 0, 0, 0, 0, 0, 0};
         PointVals pv;
         rhs<false>(T, rc, u, du, c0, &pv);
         Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 1.0 / pv.Y, 0.0, rc.moded);
@@ -255,7 +255,7 @@ struct TraceArgs {
     const double* psi_edges;          // [n_psi]
     double* bins;                     // [n_psi] weighted shell power, [n_psi] = sum w_i P_i, [n_psi+1] = sum w_i
     unsigned long long* next_ray;     // work queue head
-    unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok, n_prune
+    unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok, n_prune, n_askip
 };
 
 __device__ __forceinline__ double eps_of(double x) {  // Julia eps(x)
@@ -323,12 +323,12 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     double k_loc[S][7];
 #define KK(j, i) k_loc[j][i]
 #endif
-    __shared__ unsigned long long s_cnt[7];
+    __shared__ unsigned long long s_cnt[8];
     __shared__ double s_tot[2];
     __shared__ double s_a[7][7], s_bt[7];
     const int n_psi = a.n_psi;
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x) s_bins[j] = 0.0;
-    if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
     if (threadIdx.x < 49) s_a[threadIdx.x / 7][threadIdx.x % 7] = c_tab[SCH].a[threadIdx.x / 7][threadIdx.x % 7];
     if (threadIdx.x < 7) s_bt[threadIdx.x] = c_tab[SCH].bt[threadIdx.x];
@@ -357,9 +357,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     double err[7] = {0, 0, 0, 0, 0, 0, 0};
 #endif
     int seg = 0, npts = 0, rstat = 0, nstep = 0, last_stat = 0;
+    bool a_skip = false, a_skip_next = false;
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
-    Counters cnt = {0, 0, 0, 0, 0, 0};
+    Counters cnt = {0, 0, 0, 0, 0, 0, 0};
     double tot_dep = 0.0, tot_w = 0.0;
     unsigned int rays_ok = 0;
     long long tj = -1;  // index into the trajectory window or -1
@@ -424,6 +425,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     put_point(0.0, xl, 1.0, 0.0);
                     put_point(s0, u, 1.0, 0.0);
                     phase = PH_SEED;
+                    a_skip = false;
                 }
             }
         }
@@ -431,7 +433,14 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
         // ---- the one RHS evaluation of this trip (reference src/solve.jl:85-95), warp-converged
         double out[9];
-        if (phase != PH_IDLE) rhs<true, TORJ_PSI_IN_RHS != 0>(T, rc, tmp, out, cnt);
+        // alpha is evaluated in full at the FSAL stage (= first stage of the next step) and in the seed / callback /
+        // initial-dt phases; the inner stages take alpha = 0 when that evaluation found every harmonic negligible
+        // with a 1e10 margin (abs_albajar)
+        if (phase != PH_IDLE) {
+            const bool inner = (phase == PH_STAGE && st < S - 1);
+            rhs<true, TORJ_PSI_IN_RHS != 0>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
+            if (!inner) a_skip = a_skip_next;
+        }
 #if !TORJ_PSI_IN_RHS
         auto psi_here = [&](const double* xx, const double* dir) {  // psi_N and grad(psi_N).dx/ds at xx
             double R = sqrt(xx[0] * xx[0] + xx[1] * xx[1]), pR, pZ;
@@ -640,25 +649,25 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     }
 
     // ---- block reduction: warp shuffles, shared-memory atomics, then global atomics
-    unsigned long long c6[7] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok, cnt.n_prune};
+    unsigned long long c6[8] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok, cnt.n_prune, cnt.n_askip};
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         tot_dep += __shfl_down_sync(FULL, tot_dep, off);
         tot_w += __shfl_down_sync(FULL, tot_w, off);
 #pragma unroll
-        for (int q = 0; q < 7; ++q) c6[q] += __shfl_down_sync(FULL, c6[q], off);
+        for (int q = 0; q < 8; ++q) c6[q] += __shfl_down_sync(FULL, c6[q], off);
     }
     if (lane == 0) {
         atomicAdd(&s_tot[0], tot_dep);
         atomicAdd(&s_tot[1], tot_w);
 #pragma unroll
-        for (int q = 0; q < 7; ++q) atomicAdd(&s_cnt[q], c6[q]);
+        for (int q = 0; q < 8; ++q) atomicAdd(&s_cnt[q], c6[q]);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x)
         if (s_bins[j] != 0.0) atomicAdd(&a.bins[j], s_bins[j]);
     if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
-    if (threadIdx.x < 7) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < 8) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
 #undef KK
 }
 
@@ -680,7 +689,7 @@ __global__ void k_probe(DevTables T, long long n, const double* x, const double*
     if (i >= n) return;
     RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double u[7] = {x[i], x[n + i], x[2 * n + i], N[i], N[n + i], N[2 * n + i], 1.0}, du[7];
-    Counters c = {0, 0, 0, 0, 0, 0};
+    Counters c = {0, 0, 0, 0, 0, 0, 0};
     PointVals pv;
     rhs<true>(T, rc, u, du, c, &pv);
     double Babs = pv.Y / rc.cY;
@@ -699,7 +708,7 @@ __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int m
     RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double uu[7], dd[7];
     for (int q = 0; q < 7; ++q) uu[q] = u[(size_t)q * n + i];
-    Counters c = {0, 0, 0, 0, 0, 0};
+    Counters c = {0, 0, 0, 0, 0, 0, 0};
     rhs<true>(T, rc, uu, dd, c);
     for (int q = 0; q < 7; ++q) du[(size_t)q * n + i] = dd[q];
 }
