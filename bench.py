@@ -45,6 +45,33 @@ def bundle_for_rank(rank, small=False):
     return tj.launch_peripheral_rays(x0, N0, 0.0174, 1 / 3.99, WORKLOAD["f"], N_rings=nr, min_azimuthal_points=ma)
 
 
+def sweep_bundle(rank, world):
+    """BASELINE.json configs[3]: 32 x 32 launcher angles (pol 10..40 deg, tor -15..15 deg) x 1 025-ray beams =
+    1 049 600 rays, sharded by contiguous ray blocks over the ranks (strong scaling)."""
+    import torj_jl_b200 as tj
+    from torj_jl_b200.distributed import shard_range
+    x0 = np.array([2.5, 0.0, 0.4])
+    P, D, W = [], [], []
+    for pol in np.deg2rad(np.linspace(10.0, 40.0, 32)):
+        for tor in np.deg2rad(np.linspace(-15.0, 15.0, 32)):
+            p, d, w = tj.launch_peripheral_rays(x0, tj.pol_tor_angles_2_vector(pol, tor), 0.0174, 1 / 3.99, WORKLOAD["f"],
+                                                N_rings=7, min_azimuthal_points=20)
+            P.append(p); D.append(d); W.append(w / 1024.0)
+    P, D, W = np.concatenate(P), np.concatenate(D), np.concatenate(W)
+    lo, hi = shard_range(len(W), rank, world)
+    return P[lo:hi], D[lo:hi], W[lo:hi], len(W)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_trace per launch, from the committed ncu --set full capture of
+    this command (profiles/ktrace_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ktrace_traffic.json")) as fh:
+            return float(json.load(fh)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -128,6 +155,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="1 025-ray bundle (configs[1]) instead of 65 543 (profiling aid)")
+    ap.add_argument("--workload", default="beam64k", choices=["beam64k", "sweep1m"],
+                    help="beam64k: configs[2], weak scaling (default); sweep1m: configs[3], 1 049 600 rays, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -153,7 +182,10 @@ def main():
     tj.abs_Al_init(WORKLOAD["n_gl"], ctx)
     pl = tj.Plasma(*tj.solovev_arrays(257, 257).values())
     ph = pl.handle(ctx)
-    pos, dirs, w = bundle_for_rank(rank, args.small)
+    if args.workload == "sweep1m":
+        pos, dirs, w, n_total = sweep_bundle(rank, world)
+    else:
+        pos, dirs, w = bundle_for_rank(rank, args.small)
     n = len(w)
     psi = np.ascontiguousarray(np.linspace(0.0, 1.0, WORKLOAD["n_psi"]))
     n_psi = len(psi)
@@ -206,7 +238,8 @@ def main():
     status = np.zeros(n, dtype=np.int32)
     _lib.check(L.torj_bundle_results(bh, None, C.byref(dep), None, None, None, status.ctypes.data_as(_lib.c_ip), C.byref(cnt)))
     c = cnt.as_dict()
-    assert (status == 0).all() and c["n_rays_ok"] == n, "bench bundle has failed rays"
+    if args.workload == "beam64k":
+        assert (status == 0).all() and c["n_rays_ok"] == n, "bench bundle has failed rays"
 
     # ---- end to end through the reference-facing call with HOST buffers (H2D of the bundle, D2H of the results)
     def e2e_step():
@@ -243,13 +276,15 @@ def main():
         _lib.check(L.torj_fp64_peak(ctx, 20000, C.byref(tf), C.byref(tms)))
         achieved = algorithmic_flops(c) / (ms_per_step * 1e-3) / 1e12
         roof = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-                "traffic": None, "kernel": "k_trace<Tsit5>",
+                "traffic": ncu_traffic(), "kernel": "k_trace<Tsit5>",
                 "peak_source": "DFMA-chain microbenchmark torj_fp64_peak measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_launch": algorithmic_flops(c), "counters": c}
         line = {"metric": "ray-steps/s", "value": steps_all / (ms_per_step * 1e-3), "unit": "ray-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "config2_1k_ray_beam" if args.small else WORKLOAD["name"], "n_rays_per_gpu": n,
+                "scaling": "strong" if args.workload == "sweep1m" else "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "config4_1M_ray_angle_sweep" if args.workload == "sweep1m" else
+                           ("config2_1k_ray_beam" if args.small else WORKLOAD["name"]), "n_rays_per_gpu": n,
                            "grid": WORKLOAD["grid"], "s_max": WORKLOAD["s_max"], "n_psi": n_psi, "f": WORKLOAD["f"],
                            "mode": WORKLOAD["mode"], "scheme": "Tsit5", "l2": "compute-bound kernel; tables 4.8 MB resident, "
                            "no L2 flush needed (inputs are re-read from HBM each step: ray state 7.3 MB)"},

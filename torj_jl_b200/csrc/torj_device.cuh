@@ -694,7 +694,7 @@ __device__ __forceinline__ void depo_step(DepoState& st, const double* __restric
         for (int it = 0; it < 3; ++it) {
             double f = hermite(psi_a, psi_b, dpsi_a, dpsi_b, h, th) - gl;
             double d = hermite_d(psi_a, psi_b, dpsi_a, dpsi_b, h, th);
-            if (d != 0.0) th -= f / d;
+            if (d != 0.0) th -= f * rcp_fast(d);
             th = fmin(1.0, fmax(0.0, th));
         }
         double Pc = hermite(P_a, P_b, dP_a, dP_b, h, th);

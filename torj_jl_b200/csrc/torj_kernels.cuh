@@ -343,6 +343,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
     // q = EEst^beta1 / qold^beta2 / gamma <= 1  <=>  EEst^7 <= gamma^(10 k) qold^4   (beta1 = 7/(10k), beta2 = 4/(10k))
     const double gamma_pow = pow(gamma_c, 10.0 * ORDER);
+    const double dtmax_pow = pow(O.dtmax, -(double)ORDER);
     const double s_step = O.s_max / (double)O.n_segments;
 
     // per-lane ray state
@@ -472,8 +473,14 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             double d2 = rms7(v) / dt0;
             double md = fmax(d1, d2);
             // 10^(-(2 + log10 md)/order) = (100 md)^(-1/order)
-            double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow_nl(100.0 * md, -1.0 / (double)ORDER);
-            dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
+            // dt1 = 10^(-(2 + log10 md)/order) = (100 md)^(-1/order) >= dtmax  <=>  100 md <= dtmax^-order: the usual
+            // case (dt = dtmax) needs no pow()
+            if (md > 1e-15 && 100.0 * md <= dtmax_pow && 100.0 * dt0 >= O.dtmax) {
+                dt = O.dtmax;
+            } else {
+                double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow_nl(100.0 * md, -1.0 / (double)ORDER);
+                dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
+            }
             act = ACT_BEGIN_STEP;
         } else if (phase == PH_STAGE) {
             {
@@ -527,10 +534,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     double EEst = rms7(at);
                     if (EEst <= 1.0) {
                         cnt.n_acc++;
+                        double ttmp = t + dt;
+                        if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
                         // dt/q >= dt whenever q <= 1; at dt == dtmax the proposal is clipped back to dtmax, so the
-                        // two pow() are needed only when the step must shrink or has to grow back
+                        // two pow() are needed only when the step must shrink or has to grow back. After the last
+                        // step of a segment the proposal is never used (the next segment is a fresh problem).
                         const double e2 = EEst * EEst, q2 = qold * qold;
-                        if (dt == O.dtmax && e2 * e2 * e2 * EEst <= gamma_pow * (q2 * q2)) {
+                        if (ttmp == tstop || (dt == O.dtmax && e2 * e2 * e2 * EEst <= gamma_pow * (q2 * q2))) {
                             dtnew = dt;
                         } else {
                             double qq = 1.0 / qmax;
@@ -541,8 +551,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                             dtnew = dt / qq;
                         }
                         qold = fmax(EEst, qoldinit);
-                        double ttmp = t + dt;
-                        if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
                         hstep = ttmp - t;
                         P_a = u[6]; dP_a = KK(0, 6);
                         t = ttmp;
