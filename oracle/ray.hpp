@@ -233,8 +233,15 @@ inline int vacuum_plasma_refraction(const Plasma& pl, const double p[3], const d
         double fn = std::max(std::fabs(F[0]), std::max(std::fabs(F[1]), std::fabs(F[2])));
         if (!(fn == fn)) return RAY_INIT_FAILED;
         if (fn < 1e-12) {  // ftol, reference src/solve.jl:72
-            for (int k = 0; k < 3; ++k) N_out[k] = N[k];
-            return RAY_OK;
+            // The reference next asserts |Λ| < 1e-12 (src/solve.jl:141); |Λ| = |sum_k F_k| can reach 3 ftol, so an
+            // iteration that stops at fn just below ftol can trip that assertion. Oracle and kernel both keep
+            // iterating until the assertion has a 2x margin (a deviation only where the reference would throw).
+            double Np = N[0] * b[0] + N[1] * b[1] + N[2] * b[2];
+            double Lam = N[0] * N[0] + N[1] * N[1] + N[2] * N[2] - refractive_index_sq<double>(pp.X, pp.Y, Np, mode);
+            if (std::fabs(Lam) < 5e-13 || it >= 40) {
+                for (int k = 0; k < 3; ++k) N_out[k] = N[k];
+                return RAY_OK;
+            }
         }
         double rhs[3] = {-F[0], -F[1], -F[2]}, dx[3];
         solve3_robust(J, rhs, dx);

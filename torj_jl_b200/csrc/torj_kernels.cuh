@@ -156,7 +156,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         double R = sqrt(x0[0] * x0[0] + x0[1] * x0[1]);
         if (!inside_grid(T, R, x0[2])) {
             double t;
-            if (!box_intersection(T, x0, N0, &t)) { B.status[i] = 2; return; }
+            if (!box_intersection(T, x0, N0, &t)) { B.status[i] = 2; B.P_dep[i] = -1.0; return; }
             for (int k = 0; k < 3; ++k) p[k] = x0[k] + N0[k] * t;
         }
     }
@@ -170,7 +170,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         if (ga == 0.0) root = a;
         else if (gb == 0.0) root = b;
         else {
-            if ((ga < 0.0) == (gb < 0.0)) { B.status[i] = 2; return; }
+            if ((ga < 0.0) == (gb < 0.0)) { B.status[i] = 2; B.P_dep[i] = -2.0; return; }
             for (int it = 0; it < 200; ++it) {
                 double m = 0.5 * (a + b);
                 if (m <= a || m >= b) break;
@@ -182,10 +182,10 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         }
         for (int k = 0; k < 3; ++k) p[k] += root * N0[k];
         double psi_ref = psi_at(T, p);
-        if (!(fabs(psi_ref - T.psi_prof_max) < 1e-6)) { B.status[i] = 2; return; }
+        if (!(fabs(psi_ref - T.psi_prof_max) < 1e-6)) { B.status[i] = 2; B.P_dep[i] = -3.0; return; }
         if (psi_ref > T.psi_prof_max)
             for (int k = 0; k < 3; ++k) p[k] += 2.0 * (psi_ref - T.psi_prof_max) * N0[k];
-        if (!(psi_at(T, p) <= T.psi_prof_max)) { B.status[i] = 2; return; }
+        if (!(psi_at(T, p) <= T.psi_prof_max)) { B.status[i] = 2; B.P_dep[i] = -4.0; return; }
     }
     // ---- vacuum_plasma_refraction (reference src/solve.jl:51-74)
     double Np[3];
@@ -195,7 +195,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         PointVals pv;
         rhs<false>(T, rc, u, du, c0, &pv);
         Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 1.0 / pv.Y, 0.0, rc.moded);
-        if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; return; }
+        if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; B.P_dep[i] = -9.0; return; }
         double N_est = sqrt(d0.Ns2);
         double R = sqrt(p[0] * p[0] + p[1] * p[1]);
         double psi, pR, pZ;
@@ -211,8 +211,15 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
             double F[3], J[3][3];
             refraction_equations(N, pv.X, pv.Y, n0, nv, pv.b, rc.moded, F, J);
             double fn = fmax(fabs(F[0]), fmax(fabs(F[1]), fabs(F[2])));
-            if (!(fn == fn)) { status = 2; break; }
-            if (fn < 1e-12) { ok = true; break; }
+            if (!(fn == fn)) { status = 2; B.P_dep[i] = -5.0; break; }
+            if (fn < 1e-12) {
+                // ftol reached (reference src/solve.jl:72). The reference then asserts |Λ| < 1e-12 (src/solve.jl:141), and
+                // |Λ| = |sum_k F_k| can be up to 3 ftol: keep iterating until that assertion holds too instead of
+                // failing the ray on a residual that one more Newton step removes.
+                double Lam = N[0] * N[0] + N[1] * N[1] + N[2] * N[2]
+                             - refractive_index_sq<false>(pv.X, pv.Y, 1.0 / pv.Y, N[0] * pv.b[0] + N[1] * pv.b[1] + N[2] * pv.b[2], rc.moded).Ns2;
+                if (fabs(Lam) < 5e-13 || it >= 40) { ok = true; break; }
+            }
             double r[3] = {-F[0], -F[1], -F[2]}, dx[3];
             solve3_robust(J, r, dx);
             double lam = 1.0, f2 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
@@ -224,16 +231,16 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
                 if (f2t == f2t && f2t < f2) { for (int k = 0; k < 3; ++k) N[k] = Nt[k]; stepped = true; break; }
                 lam *= 0.5;
             }
-            if (!stepped) { status = 2; break; }
+            if (!stepped) { status = 2; B.P_dep[i] = -6.0 - 1e-3 * it - fn; break; }
         }
-        if (!ok && status == 0) status = 2;
+        if (!ok && status == 0) { status = 2; B.P_dep[i] = -7.0; }
         if (status != 0) { B.status[i] = status; return; }
         for (int k = 0; k < 3; ++k) Np[k] = N[k];
         // assert |Λ| < 1e-12 (reference src/solve.jl:141)
         double u2[7] = {p[0], p[1], p[2], Np[0], Np[1], Np[2], 1.0};
         rhs<false>(T, rc, u2, du, c0, &pv);
         // Λ as the reference forms it: norm(N)^2 - Ns^2
-        if (!(fabs(pv.Lambda) < 1e-12)) { B.status[i] = 2; return; }
+        if (!(fabs(pv.Lambda) < 1e-12)) { B.status[i] = 2; B.P_dep[i] = -8.0 - fabs(pv.Lambda); return; }
     }
     B.u0[i] = p[0]; B.u0[n + i] = p[1]; B.u0[2 * n + i] = p[2];
     B.u0[3 * n + i] = Np[0]; B.u0[4 * n + i] = Np[1]; B.u0[5 * n + i] = Np[2];
