@@ -150,6 +150,8 @@ int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int
 /* --- measurement ------------------------------------------------------------------------------------------- */
 /* Register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). */
 int torj_fp64_peak(torj_ctx* ctx, int32_t iters, double* tflops, double* ms);
+/* Dependent-issue latency of DFMA in cycles (one warp, one chain): how much ILP x TLP the FP64 pipe needs. */
+int torj_fp64_latency(torj_ctx* ctx, int32_t iters, double* cycles_per_dfma);
 
 #ifdef __cplusplus
 }

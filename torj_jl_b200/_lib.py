@@ -67,6 +67,7 @@ SIGNATURES = {
                              C.c_double, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip, C.c_int64, C.c_int64,
                              C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TorjCounters)]),
     "torj_fp64_peak": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
+    "torj_fp64_latency": (C.c_int, [c_vp, C.c_int32, c_dp]),
 }
 
 

@@ -158,6 +158,13 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
     for (int n = 0; n < 5; ++n)
         for (int k = 0; k < TORJ_BESS_K; ++k) bd[n][k] = (double)(n + 2 * k) * bc[n][k];
     CK(cudaMemcpyToSymbol(c_bessd, bd, sizeof bd));
+    {   // exp_fast: range reduction constants and Taylor coefficients 1/13! ... 1/2!, 1/1!, 1/0!
+        double ce[17] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+        double fact = 1.0, inv[14];
+        for (int n = 0; n <= 13; ++n) { if (n > 0) fact *= (double)n; inv[n] = 1.0 / fact; }
+        for (int j = 0; j <= 13; ++j) ce[3 + j] = inv[13 - j];
+        CK(cudaMemcpyToSymbol(c_exp, ce, sizeof ce));
+    }
     *out = c;
     return 0;
 }
@@ -633,6 +640,22 @@ int torj_fp64_peak(torj_ctx* c, int32_t iters, double* tflops, double* ms) {
     if (ms) *ms = t;
     if (tflops) *tflops = flops / (t * 1e-3) / 1e12;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return 0;
+}
+
+// cycles per dependent DFMA (single warp, single chain)
+int torj_fp64_latency(torj_ctx* c, int32_t iters, double* cycles_per_dfma) {
+    if (set_device(c)) return 1;
+    double* d; long long* dc;
+    CK(cudaMalloc(&d, sizeof(double)));
+    CK(cudaMalloc(&dc, sizeof(long long)));
+    k_dfma_latency<<<1, 32, 0, c->stream>>>(iters, 1.0, d, dc);
+    c->launches++;
+    long long cyc = 0;
+    CK(cudaMemcpyAsync(&cyc, dc, sizeof cyc, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *cycles_per_dfma = (double)cyc / (16.0 * (double)iters);
+    cudaFree(d); cudaFree(dc);
     return 0;
 }
 

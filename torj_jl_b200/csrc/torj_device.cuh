@@ -27,6 +27,26 @@ namespace torj {
 #ifndef TORJ_ROW_FENCE
 #define TORJ_ROW_FENCE 1
 #endif
+#ifndef TORJ_EXP_ESTRIN
+#define TORJ_EXP_ESTRIN 0
+#endif
+#ifndef TORJ_NODE_UNROLL
+#define TORJ_NODE_UNROLL 1
+#endif
+#define TORJ_STR2(x) #x
+#define TORJ_STR(x) TORJ_STR2(x)
+#define TORJ_PRAGMA_NODE_UNROLL _Pragma(TORJ_STR(unroll TORJ_NODE_UNROLL))
+#ifndef TORJ_ROW_LOOP
+#define TORJ_ROW_LOOP 0
+#endif
+#ifndef TORJ_NOINLINE_MATH
+#define TORJ_NOINLINE_MATH 0  // 1: exp/rcp/rsqrt/sqrt helpers as shared subroutines (smaller hot loop)
+#endif
+#if TORJ_NOINLINE_MATH
+#define TORJ_MATH_INLINE __noinline__
+#else
+#define TORJ_MATH_INLINE __forceinline__
+#endif
 #define TORJ_BESS_K 24
 
 struct DevTables {
@@ -89,7 +109,7 @@ struct Counters {
 // instructions and carry a slow-path branch each; the hot path has ~25 of them per RHS.  Arguments here are
 // normal, positive (or non-zero for rcp) numbers; zero is handled where it can occur (sqrt_fast).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rcp_fast(double x) {
+__device__ TORJ_MATH_INLINE double rcp_fast(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
@@ -97,7 +117,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-__device__ __forceinline__ double rsqrt_fast(double x) {
+__device__ TORJ_MATH_INLINE double rsqrt_fast(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x * y, 0.5 * y, 0.5);
@@ -105,7 +125,7 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
     e = fma(-x * y, 0.5 * y, 0.5);
     return fma(y, e, y);
 }
-__device__ __forceinline__ double sqrt_fast(double x) {  // x >= 0
+__device__ TORJ_MATH_INLINE double sqrt_fast(double x) {  // x >= 0
     double y = rsqrt_fast(x);
     double s = x * y;
     s = fma(fma(-s, s, x), 0.5 * y, s);
@@ -153,8 +173,18 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
     int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
     double v[4] = {0, 0, 0, 0}, vR[4] = {0, 0, 0, 0}, vZ[4] = {0, 0, 0, 0};
     double te = 0.0, ps = 0.0, psR = 0.0, psZ = 0.0;
+#if TORJ_ROW_LOOP
+    // rows as a real loop (4x less code for the 16-node stencil: the hot loop has to fit the instruction cache);
+    // the row weights are picked from registers with selects instead of indexing a local array
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const double wzj = j == 0 ? wz[0] : (j == 1 ? wz[1] : (j == 2 ? wz[2] : wz[3]));
+        const double dwzj = j == 0 ? dwz[0] : (j == 1 ? dwz[1] : (j == 2 ? dwz[2] : dwz[3]));
+#else
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        const double wzj = wz[j], dwzj = dwz[j];
+#endif
         size_t node = (size_t)(bz + j) * T.row + br;
         const double2* pa = T.A + 2 * node;
         const double2* pb = T.B + node;
@@ -174,12 +204,12 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            v[q] = fma(wz[j], a[q], v[q]);
-            vR[q] = fma(wz[j], aR[q], vR[q]);
-            vZ[q] = fma(dwz[j], a[q], vZ[q]);
+            v[q] = fma(wzj, a[q], v[q]);
+            vR[q] = fma(wzj, aR[q], vR[q]);
+            vZ[q] = fma(dwzj, a[q], vZ[q]);
         }
-        te = fma(wz[j], at, te);
-        if (WITH_PSI) { ps = fma(wz[j], ap, ps); psR = fma(wz[j], apR, psR); psZ = fma(dwz[j], ap, psZ); }
+        te = fma(wzj, at, te);
+        if (WITH_PSI) { ps = fma(wzj, ap, ps); psR = fma(wzj, apR, psR); psZ = fma(dwzj, ap, psZ); }
 #if TORJ_ROW_FENCE
         // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
         // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
@@ -367,26 +397,36 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
 // non-positive exponents whose values below e^-708 cannot matter next to alpha_floor).
 // k = rint(x log2 e), r = x - k ln2 (two-part), degree-13 Taylor polynomial on |r| <= ln2/2 (remainder < 4e-18),
 // scaled by 2^k built in the exponent field.
-__device__ __forceinline__ double exp_fast(double x) {
+__constant__ double c_exp[17];  // log2(e), -ln2_hi, -ln2_lo, 1/13!, 1/12!, ..., 1/2!, 1, 1 (constant-bank operands: a
+                                // 64-bit literal costs two extra issue slots per use, a c[][] operand none)
+__device__ TORJ_MATH_INLINE double exp_fast(double x) {
     x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
     x = x > 708.0 ? 708.0 : x;
-    const double kd = rint(x * 1.4426950408889634074);
-    double r = fma(kd, -6.93147180369123816490e-01, x);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double kd = rint(x * c_exp[0]);
+    double r = fma(kd, c_exp[1], x);
+    r = fma(kd, c_exp[2], r);
+#if TORJ_EXP_ESTRIN
+    // Estrin evaluation of sum_{n=0}^{13} r^n/n!: dependency depth 5 instead of 13 (DFMA latency is 8 cycles and
+    // only two warps share a scheduler). c_exp[16-n] = 1/n!.
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double q0 = fma(c_exp[15], r, c_exp[16]);   // 1 + r
+    const double q1 = fma(c_exp[13], r, c_exp[14]);   // 1/2! + r/3!
+    const double q2 = fma(c_exp[11], r, c_exp[12]);
+    const double q3 = fma(c_exp[9], r, c_exp[10]);
+    const double q4 = fma(c_exp[7], r, c_exp[8]);
+    const double q5 = fma(c_exp[5], r, c_exp[6]);
+    const double q6 = fma(c_exp[3], r, c_exp[4]);     // 1/12! + r/13!
+    const double s0 = fma(q1, r2, q0);                // degrees 0..3
+    const double s1 = fma(q3, r2, q2);                // 4..7
+    const double s2 = fma(q5, r2, q4);                // 8..11
+    const double t0 = fma(s1, r4, s0);                // 0..7
+    const double t1 = fma(q6, r4, s2);                // 8..13
+    const double p = fma(t1, r8, t0);
+#else
+    double p = c_exp[3];
+#pragma unroll
+    for (int i = 4; i < 17; ++i) p = fma(p, r, c_exp[i]);
+#endif
     const int k = (int)kd;  // in [-1022, 1022]
     return p * __hiloint2double((k + 1023) << 20, 0);
 }
@@ -427,7 +467,7 @@ template <int M, int K, bool GENERIC>
 __device__ __forceinline__ double harmonic_sum(const HarmCoef& c) {
     double sum = 0.0;
     const int n = c_gl.n;
-#pragma unroll 1
+    TORJ_PRAGMA_NODE_UNROLL
     for (int k = 0; k < n; ++k) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
         const double ex = exp_fast(fma(c.e1, t, c.e0));

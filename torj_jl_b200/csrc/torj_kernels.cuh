@@ -744,4 +744,17 @@ __global__ void k_dfma(int iters, double* out) {
     if (s == 12345.6789) out[0] = s;
 }
 
+// dependent-issue latency of DFMA: one warp, one chain, cycles from clock64()
+__global__ void k_dfma_latency(int iters, double seed, double* out, long long* cycles) {
+    double a = seed;
+    const double m = 0.999999, c = 1e-7;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a = fma(a, m, c);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { cycles[0] = t1 - t0; out[0] = a; }
+}
+
 }  // namespace torj
