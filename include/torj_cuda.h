@@ -123,12 +123,17 @@ int torj_bundle_create(torj_ctx* ctx, int64_t n_rays, const double* pos, const d
 void torj_bundle_destroy(torj_bundle* b);
 /* Trajectories are kept for rays [traj_first, traj_first+traj_count), up to traj_max_pts points each. */
 int torj_bundle_set_window(torj_bundle* b, int64_t traj_first, int64_t traj_count, int32_t traj_max_pts);
+/* Scans: rays of several beams (launchers, frequencies) in one bundle, one deposition profile per beam — the batched
+ * form of a host loop over make_beam (reference src/solve.jl:209-242). beam_id[n] in [0, n_beams); n_beams = 1 or a
+ * NULL beam_id restores the single profile. With n_beams > 1 dP_dV is [n_beams][n_psi], deposited_power [n_beams] and
+ * the device profile [n_beams][n_psi+2]. */
+int torj_bundle_set_beams(torj_bundle* b, int32_t n_beams, const int32_t* beam_id);
 /* Enqueues ray init + trace + profile finalize on the context stream; returns without synchronising.
  * Replaces the parallel region and reduction of make_beam (reference src/solve.jl:219-240) and, per ray,
  * make_ray (src/solve.jl:135-181) incl. power_deposition_profile (src/plasma.jl:91-151). */
 int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* opt, double s_max, int32_t n_psi,
                       const double* psi_edges);
-/* Device pointer to n_psi+2 doubles: dP_dV[n_psi], deposited_power, sum of weights — for a caller-side
+/* Device pointer to n_beams x (n_psi+2) doubles: dP_dV[n_psi], deposited_power, sum of weights per beam — for a caller-side
  * NCCL all-reduce (sum) across GPUs; valid after torj_bundle_trace, ordered on the context stream. */
 void* torj_bundle_device_profile(torj_bundle* b);
 /* Synchronises and copies results to the host (any pointer may be NULL). */
@@ -141,7 +146,7 @@ int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, 
 /* --- one-shot host-buffer call: what the Julia make_ray / make_beam shims ccall ------------------------------ */
 int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
                const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
-               double s_max, int32_t n_psi, const double* psi_edges,
+               double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id /* or NULL */,
                /* out */ double* dP_dV, double* deposited_power, double* P_final, double* P_deposited_ray,
                int32_t* n_points, int32_t* status,
                /* optional trajectories */ int64_t traj_first, int64_t traj_count, int32_t traj_max_pts, double* traj_s,

@@ -272,6 +272,30 @@ def test_per_ray_frequency_and_mode(gpu_small, oracle_small, gl24, launcher):
     assert l2rel(res["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
 
 
+def test_batched_beams_equal_separate_calls(gpu_small, oracle_small, gl24, launcher):
+    """make_beams: three launchers (angles, frequency, mode differ) in one device call == three make_beam-style calls."""
+    psi = np.linspace(0, 1, 150)
+    base = dict(r=2.5, phi=0.0, z=0.4, spot_size=launcher["spot"], inverse_curvature_radius=launcher["inv_Rc"])
+    Ls = [dict(base, steering_angle_pol=np.deg2rad(30.0), steering_angle_tor=0.0, f=95e9, mode=1),
+          dict(base, steering_angle_pol=np.deg2rad(24.0), steering_angle_tor=0.12, f=110e9, mode=1),
+          dict(base, steering_angle_pol=np.deg2rad(33.0), steering_angle_tor=-0.08, f=95e9, mode=-1)]
+    dP, dep, W, Pf, res = tj.make_beams(gpu_small, Ls, 0.6, psi)
+    assert dP.shape == (3, 150) and dep.shape == (3,) and (res["status"] == 0).all()
+    for b, L in enumerate(Ls):
+        N0 = tj.pol_tor_angles_2_vector(L["steering_angle_pol"], L["steering_angle_tor"])
+        pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], N0, L["spot_size"], L["inverse_curvature_radius"], L["f"])
+        one = tj.trace_bundle(gpu_small, pos, dirs, w, L["f"], L["mode"], 0.6, psi)
+        assert np.array_equal(one["P_final"], Pf[b])
+        assert np.abs(one["dP_dV"] - dP[b]).max() <= 1e-12 * max(1e-300, np.abs(one["dP_dV"]).max())
+        assert abs(one["deposited_power"] - dep[b]) < 1e-13
+        ref = oracle_small.trace_bundle(pos, dirs, w, L["f"], L["mode"], 0.6, psi, gl24)
+        assert abs(dep[b] - ref["deposited_power"]) <= FRAC_TOL * max(ref["deposited_power"], 1e-12)
+        if ref["deposited_power"] > 1e-6:
+            assert l2rel(dP[b], ref["dP_dV"]) < L2_FAITHFUL
+    with pytest.raises(tj.TorjError, match="beam_id out of range"):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.1, psi, beam_id=[3], n_beams=2)
+
+
 def test_smallest_inputs(gpu_small, launcher):
     r = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 1.0]))
     assert r["status"][0] == 0 and r["dP_dV"].shape == (2,) and r["dP_dV"][1] == 0.0

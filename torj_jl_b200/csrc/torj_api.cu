@@ -76,6 +76,9 @@ struct torj_bundle {
     // what the device copies of psi_edges / dV were computed from (skips the re-upload when unchanged)
     std::vector<double> h_edges;
     uint64_t edges_plasma = 0;
+    // beams
+    int n_beams = 1, prof_rows = 0;
+    int* d_beam = nullptr;
 };
 
 static int set_device(const torj_ctx* c) {
@@ -429,6 +432,7 @@ void torj_bundle_destroy(torj_bundle* b) {
     cudaFree(b->d_s0); cudaFree(b->d_psil); cudaFree(b->d_Pf); cudaFree(b->d_Pdep); cudaFree(b->d_status); cudaFree(b->d_npts);
     cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
     cudaFree(b->d_profile);
+    cudaFree(b->d_beam);
     free_traj(b);
     delete b;
 }
@@ -448,6 +452,23 @@ int torj_bundle_set_window(torj_bundle* b, int64_t first, int64_t count, int32_t
     return 0;
 }
 
+int torj_bundle_set_beams(torj_bundle* b, int32_t n_beams, const int32_t* beam_id) {
+    torj_ctx* c = b->ctx;
+    if (n_beams < 1) FAIL("torj_bundle_set_beams: n_beams < 1");
+    if (set_device(c)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_beams == 1 || !beam_id) {
+        b->n_beams = 1;
+        return 0;
+    }
+    for (int64_t i = 0; i < b->n; ++i)
+        if (beam_id[i] < 0 || beam_id[i] >= n_beams) FAIL("torj_bundle_set_beams: beam_id out of range");
+    if (!b->d_beam) CK(cudaMalloc(&b->d_beam, b->n * sizeof(int)));
+    CK(cudaMemcpy(b->d_beam, beam_id, b->n * sizeof(int), cudaMemcpyHostToDevice));
+    b->n_beams = n_beams;
+    return 0;
+}
+
 int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* opt, double s_max, int32_t n_psi,
                       const double* psi_edges) {
     torj_ctx* c = b->ctx;
@@ -462,14 +483,16 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
-    if (b->n_psi != n_psi) {
+    if (b->n_psi != n_psi || b->prof_rows != b->n_beams) {
         CK(cudaStreamSynchronize(st));
         cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV); cudaFree(b->d_profile);
+        b->h_edges.clear();
         CK(cudaMalloc(&b->d_edges, n_psi * sizeof(double)));
-        CK(cudaMalloc(&b->d_bins, (n_psi + 2) * sizeof(double)));
+        CK(cudaMalloc(&b->d_bins, (size_t)b->n_beams * (n_psi + 2) * sizeof(double)));
         CK(cudaMalloc(&b->d_dV, n_psi * sizeof(double)));
-        CK(cudaMalloc(&b->d_profile, (n_psi + 2) * sizeof(double)));
+        CK(cudaMalloc(&b->d_profile, (size_t)b->n_beams * (n_psi + 2) * sizeof(double)));
         b->n_psi = n_psi;
+        b->prof_rows = b->n_beams;
     }
     if (b->traj_count > 0 && b->traj_prof_npsi != n_psi) {
         CK(cudaStreamSynchronize(st));
@@ -487,7 +510,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         b->h_edges.assign(psi_edges, psi_edges + n_psi);
         b->edges_plasma = p->id;
     }
-    CK(cudaMemsetAsync(b->d_bins, 0, (n_psi + 2) * sizeof(double), st));
+    CK(cudaMemsetAsync(b->d_bins, 0, (size_t)b->n_beams * (n_psi + 2) * sizeof(double), st));
     CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), st));
     if (b->traj_count > 0) CK(cudaMemsetAsync(b->d_tprof, 0, (size_t)b->traj_count * n_psi * sizeof(double), st));
@@ -501,7 +524,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.T = p->T; a.B = b->B; a.O = so;
     a.J.first = b->traj_first; a.J.count = b->traj_count; a.J.max_pts = b->traj_max;
     a.J.s = b->d_ts; a.J.xyz = b->d_txyz; a.J.P = b->d_tP; a.J.dP = b->d_tdP; a.J.prof = b->d_tprof;
-    a.n_psi = n_psi; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
+    a.n_psi = n_psi; a.n_beams = b->n_beams; a.beam_id = b->d_beam; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
     size_t smem = (size_t)n_psi * sizeof(double);
 #if TORJ_K_SMEM
     smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
@@ -525,7 +548,8 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, st));
     c->ev_valid = true;
-    k_finalize<<<(n_psi + 2 + 127) / 128, 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->d_profile);
+    k_finalize<<<(unsigned)(((size_t)b->n_beams * (n_psi + 2) + 127) / 128), 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->n_beams,
+                                                                                         b->d_profile);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -539,8 +563,9 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
     if (b->n_psi == 0) FAIL("torj_bundle_results: nothing traced yet");
-    std::vector<double> prof(b->n_psi + 2);
-    CK(cudaMemcpyAsync(prof.data(), b->d_profile, (b->n_psi + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const size_t row = (size_t)b->n_psi + 2;
+    std::vector<double> prof(row * b->n_beams);
+    CK(cudaMemcpyAsync(prof.data(), b->d_profile, prof.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (P_final) CK(cudaMemcpyAsync(P_final, b->d_Pf, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (P_dep) CK(cudaMemcpyAsync(P_dep, b->d_Pdep, b->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (n_points) CK(cudaMemcpyAsync(n_points, b->d_npts, b->n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -548,8 +573,10 @@ int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, 
     unsigned long long cn[8];
     CK(cudaMemcpyAsync(cn, b->d_counters, sizeof cn, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (dP_dV) memcpy(dP_dV, prof.data(), b->n_psi * sizeof(double));
-    if (deposited_power) *deposited_power = prof[b->n_psi];
+    for (int q = 0; q < b->n_beams; ++q) {
+        if (dP_dV) memcpy(dP_dV + (size_t)q * b->n_psi, prof.data() + q * row, b->n_psi * sizeof(double));
+        if (deposited_power) deposited_power[q] = prof[q * row + b->n_psi];
+    }
     if (counters) {
         counters->n_acc = (int64_t)cn[0]; counters->n_rej = (int64_t)cn[1]; counters->n_rhs = (int64_t)cn[2];
         counters->n_alpha = (int64_t)cn[3]; counters->n_harm = (int64_t)cn[4]; counters->n_rays_ok = (int64_t)cn[5];
@@ -586,8 +613,9 @@ int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, 
 
 int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
                const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
-               double s_max, int32_t n_psi, const double* psi_edges, double* dP_dV, double* deposited_power,
-               double* P_final, double* P_dep, int32_t* n_points, int32_t* status, int64_t traj_first, int64_t traj_count,
+               double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id, double* dP_dV,
+               double* deposited_power, double* P_final, double* P_dep, int32_t* n_points, int32_t* status, int64_t traj_first,
+               int64_t traj_count,
                int32_t traj_max_pts, double* traj_s, double* traj_xyz, double* traj_P, double* traj_dP_ds,
                double* traj_dP_dV_ray, torj_counters* counters) {
     // the device workspace of the previous call is reused when the bundle shape is unchanged (no cudaMalloc/cudaFree
@@ -609,6 +637,7 @@ int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
     }
     if (traj_count != b->traj_count || traj_first != b->traj_first || (traj_count > 0 && traj_max_pts != b->traj_max))
         rc = torj_bundle_set_window(b, traj_first, traj_count, traj_max_pts);
+    if (!rc) rc = torj_bundle_set_beams(b, n_beams, beam_id);
     if (!rc) rc = torj_bundle_trace(b, p, opt, s_max, n_psi, psi_edges);
     if (!rc) rc = torj_bundle_results(b, dP_dV, deposited_power, P_final, P_dep, n_points, status, counters);
     if (!rc && traj_count > 0) rc = torj_bundle_trajectories(b, traj_s, traj_xyz, traj_P, traj_dP_ds, traj_dP_dV_ray);

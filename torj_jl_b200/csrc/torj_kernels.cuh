@@ -259,8 +259,10 @@ struct TraceArgs {
     SolverOpts O;
     TrajDev J;
     int n_psi;
+    int n_beams;                      // > 1: one profile per beam, booked straight into global memory
+    const int* beam_id;               // [n] (n_beams > 1 only)
     const double* psi_edges;          // [n_psi]
-    double* bins;                     // [n_psi] weighted shell power, [n_psi] = sum w_i P_i, [n_psi+1] = sum w_i
+    double* bins;                     // [n_beams][n_psi+2]: weighted shell power, then sum w_i P_i and sum w_i
     unsigned long long* next_ray;     // work queue head
     unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok, n_prune, n_askip
 };
@@ -379,8 +381,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #pragma unroll
         for (int i = 0; i < 7; ++i) KK(j, i) = 0.0;
 
+    double* beam_bins = a.bins;  // this ray's beam row (scans: rays of many launchers / frequencies in one bundle)
     auto sink = [&](int shell, double dP) {
-        atomicAdd(&s_bins[shell], wgt * dP);
+        if (a.n_beams > 1) atomicAdd(&beam_bins[shell], wgt * dP);
+        else atomicAdd(&s_bins[shell], wgt * dP);
         pdep += dP;
         if (tj >= 0) a.J.prof[tj * n_psi + shell] += dP;
     };
@@ -420,6 +424,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
                     rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
                     seg = 0; npts = 0; rstat = 0; pdep = 0.0;
+                    if (a.n_beams > 1) beam_bins = a.bins + (size_t)a.beam_id[idx] * (n_psi + 2);
                     if (TORJ_FATAL(last_stat)) {  // a dead ray may have left NaN/Inf in the stage slots (0 * NaN != 0)
 #pragma unroll
                         for (int j = 0; j < S; ++j)
@@ -623,8 +628,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     if (!TORJ_FATAL(rstat)) {
                         a.B.P_final[ray] = u[6];
                         a.B.P_dep[ray] = pdep;
-                        tot_dep += wgt * pdep;
-                        tot_w += wgt;
+                        if (a.n_beams > 1) {
+                            atomicAdd(&beam_bins[n_psi], wgt * pdep);
+                            atomicAdd(&beam_bins[n_psi + 1], wgt);
+                        } else {
+                            tot_dep += wgt * pdep;
+                            tot_w += wgt;
+                        }
                         rays_ok++;
                     }
                     ray = -1;
@@ -687,11 +697,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
-__global__ void k_finalize(const double* bins, const double* dV, int n_psi, double* profile) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_psi - 1) profile[j] = bins[j] / dV[j];
-    else if (j == n_psi - 1) profile[j] = 0.0;
-    else if (j <= n_psi + 1) profile[j] = bins[j];
+__global__ void k_finalize(const double* bins, const double* dV, int n_psi, int n_beams, double* profile) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n_beams * (n_psi + 2)) return;
+    int j = (int)(g % (n_psi + 2));
+    if (j < n_psi - 1) profile[g] = bins[g] / dV[j];
+    else if (j == n_psi - 1) profile[g] = 0.0;
+    else profile[g] = bins[g];
 }
 
 // ------------------------------------------------------------------------------------------------

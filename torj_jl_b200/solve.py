@@ -24,8 +24,9 @@ def _p(a):
 
 
 def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, mode, s_max, psi_dP_dV, *,
-                 options=None, ctx=None, trajectories=None, traj_max_pts=None):
-    """One torj_trace call on host buffers. trajectories: None or (first, count)."""
+                 options=None, ctx=None, trajectories=None, traj_max_pts=None, beam_id=None, n_beams=1):
+    """One torj_trace call on host buffers. trajectories: None or (first, count).
+    beam_id/n_beams: rays of several beams in one bundle -> dP_dV[n_beams, n_psi], deposited_power[n_beams]."""
     ctx = ctx or _lib.context()
     L = _lib.lib()
     pos = np.ascontiguousarray(np.asarray(ray_positions, dtype=np.float64).T)
@@ -37,7 +38,11 @@ def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, 
     md = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mode), fr.shape), dtype=np.int32)
     psi = np.ascontiguousarray(psi_dP_dV, dtype=np.float64)
     opt = options or _lib.default_options()
-    prof = np.zeros(len(psi)); dep = C.c_double()
+    n_beams = int(n_beams) if beam_id is not None else 1
+    bid = np.ascontiguousarray(beam_id, dtype=np.int32) if beam_id is not None else None
+    if bid is not None and bid.shape != (n,):
+        raise ValueError("beam_id must have one entry per ray")
+    prof = np.zeros((n_beams, len(psi))); dep = np.zeros(n_beams)
     Pf = np.zeros(n); Pd = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
     cnt = _lib.TorjCounters()
     t_first, t_count = trajectories if trajectories else (0, 0)
@@ -47,10 +52,11 @@ def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, 
     ts = np.zeros((t_count, tm)); txyz = np.zeros((t_count, 3, tm)); tP = np.zeros((t_count, tm))
     tdP = np.zeros((t_count, tm)); tprof = np.zeros((t_count, len(psi)))
     _lib.check(L.torj_trace(ctx, plasma.handle(ctx), C.byref(opt), n, _p(pos), _p(dr), _p(wt), _p(fr),
-                            md.ctypes.data_as(c_ip), per_ray, float(s_max), len(psi), _p(psi), _p(prof), C.byref(dep),
+                            md.ctypes.data_as(c_ip), per_ray, float(s_max), len(psi), _p(psi), n_beams,
+                            bid.ctypes.data_as(c_ip) if bid is not None else None, _p(prof), _p(dep),
                             _p(Pf), _p(Pd), npts.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip), t_first, t_count, tm,
                             _p(ts), _p(txyz), _p(tP), _p(tdP), _p(tprof), C.byref(cnt)))
-    return dict(dP_dV=prof, deposited_power=dep.value, P_final=Pf, P_deposited_ray=Pd, n_points=npts, status=st,
+    return dict(dP_dV=prof if n_beams > 1 else prof[0], deposited_power=dep if n_beams > 1 else float(dep[0]), P_final=Pf, P_deposited_ray=Pd, n_points=npts, status=st,
                 counters=cnt.as_dict(), traj_s=ts, traj_xyz=txyz, traj_P=tP, traj_dP_ds=tdP, traj_dP_dV_ray=tprof)
 
 
@@ -89,3 +95,23 @@ def make_beam(plasma: Plasma, r, phi, z, steering_angle_tor, steering_angle_pol,
         traj.append([res["traj_xyz"][i, :, k].copy() for k in range(m)])
         powers.append(res["traj_P"][i, :m].copy())
     return arc, traj, powers, res["dP_dV"], res["deposited_power"], wts
+
+
+def make_beams(plasma: Plasma, launchers, s_max, psi_dP_dV, *, options=None, ctx=None, **kwargs):
+    """Batched make_beam for scans: `launchers` is a sequence of dicts with the positional arguments of make_beam
+    (r, phi, z, steering_angle_tor, steering_angle_pol, spot_size, inverse_curvature_radius, f, mode). All beams are
+    traced in ONE device call; returns (dP_dV[n_beams, n_psi], deposited_power[n_beams], ray_weights per beam,
+    P_final per beam). Equivalent to a host loop over make_beam (reference src/solve.jl:209-242) without trajectories."""
+    P, D, W, F, M, B = [], [], [], [], [], []
+    for b, L in enumerate(launchers):
+        N0 = pol_tor_angles_2_vector(L["steering_angle_pol"], L["steering_angle_tor"])
+        x0 = np.array([L["r"] * np.cos(L["phi"]), L["r"] * np.sin(L["phi"]), L["z"]])
+        p, d, w = launch_peripheral_rays(x0, N0, L["spot_size"], L["inverse_curvature_radius"], L["f"], **kwargs)
+        P.append(p); D.append(d); W.append(w)
+        F.append(np.full(len(w), float(L["f"]))); M.append(np.full(len(w), int(L["mode"]), dtype=np.int32))
+        B.append(np.full(len(w), b, dtype=np.int32))
+    res = trace_bundle(plasma, np.concatenate(P), np.concatenate(D), np.concatenate(W), np.concatenate(F), np.concatenate(M),
+                       s_max, psi_dP_dV, options=options, ctx=ctx, beam_id=np.concatenate(B), n_beams=len(launchers))
+    off = np.cumsum([0] + [len(w) for w in W])
+    dP = np.atleast_2d(res["dP_dV"]); dep = np.atleast_1d(res["deposited_power"])
+    return dP, dep, W, [res["P_final"][off[i]:off[i + 1]] for i in range(len(W))], res
