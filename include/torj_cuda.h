@@ -106,6 +106,14 @@ int torj_plasma_create(torj_ctx* ctx, const torj_grid* grid, const double* coef_
                        const double* coef_lnTe, const double* coef_BR, const double* coef_BZ, const double* coef_Bphi,
                        const double* vol_coef, int32_t n_vol, double vol_psi0, double vol_dpsi, double psi_prof_max,
                        torj_plasma** out);
+/* The whole `Plasma(R, Z, psiN, psi_prof, ne, Te, BR, BZ, Bphi, psi1d, V1d)` constructor (reference src/plasma.jl:30-58
+ * incl. make_2d_prof_spline :16-22) from the raw arrays: 1-D resampling/log/prefilter on the host, the six 2-D
+ * prefilters and the table packing on the device. 2-D arrays are nR x nZ, R fastest. Needs nothing of
+ * Interpolations.jl's internals on the Julia side. */
+int torj_plasma_create_from_data(torj_ctx* ctx, const torj_grid* grid, const double* psi_norm, const double* psi_prof,
+                                 const double* ne_prof, const double* Te_prof, int32_t n_prof, const double* BR,
+                                 const double* BZ, const double* Bphi, const double* psi_1d, const double* vol_1d,
+                                 int32_t n_1d, torj_plasma** out);
 void torj_plasma_destroy(torj_plasma* p);
 
 /* Field probes at Cartesian points x[3][n] (tests of reference src/plasma.jl:61-89 / src/dispersion.jl:7-15,

@@ -296,6 +296,33 @@ def test_batched_beams_equal_separate_calls(gpu_small, oracle_small, gl24, launc
         tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.1, psi, beam_id=[3], n_beams=2)
 
 
+def test_device_side_plasma_construction(arrays_small, oracle_small, gl24, launcher):
+    """torj_plasma_create_from_data (prefilter + packing on the GPU, reference src/plasma.jl:16-58) against the
+    host-prefiltered tables, on a non-uniform profile grid so the natural-cubic resampling is exercised too."""
+    arr = dict(arrays_small)
+    psi = np.linspace(0, 1, 101) ** 1.3
+    arr["psi_prof"] = psi; arr["ne_prof"] = 3e19 * (1 - psi) + 1e17; arr["Te_prof"] = 4e3 * (1 - psi) ** 2 + 50
+    host = tj.Plasma(*arr.values())
+    dev = tj.Plasma(*arr.values(), build="device")
+    rng = np.random.default_rng(5)
+    R = rng.uniform(0.4, 2.8, 400); ph = rng.uniform(-3, 3, 400); Z = rng.uniform(-1.5, 1.5, 400)   # incl. off-grid points
+    X = np.stack([R * np.cos(ph), R * np.sin(ph), Z], 1)
+    N = rng.normal(size=X.shape) * 0.4
+    a = host.probe(X, N, 95e9, 1); b = dev.probe(X, N, 95e9, 1)
+    for k in ("psi", "Y", "N_par", "Lambda"):
+        assert np.abs(a[k] - b[k]).max() <= 1e-12 * max(1.0, np.abs(a[k]).max()), k
+    for k in ("ne", "Te", "X"):
+        assert (np.abs(a[k] - b[k]) / np.maximum(np.abs(a[k]), 1e-300)).max() < 1e-10, k
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    grid = np.linspace(0, 1, 100)
+    ra = tj.trace_bundle(host, pos, dirs, w, launcher["f"], 1, 0.5, grid)
+    rb = tj.trace_bundle(dev, pos, dirs, w, launcher["f"], 1, 0.5, grid)
+    assert np.array_equal(ra["n_points"], rb["n_points"]) and np.abs(ra["P_final"] - rb["P_final"]).max() < 1e-10
+    assert l2rel(rb["dP_dV"], ra["dP_dV"]) < 1e-9
+    ref = O.OraclePlasma(*arr.values()).trace_bundle(pos, dirs, w, launcher["f"], 1, 0.5, grid, gl24)
+    assert abs(rb["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+
+
 def test_smallest_inputs(gpu_small, launcher):
     r = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 1.0]))
     assert r["status"][0] == 0 and r["dP_dV"].shape == (2,) and r["dP_dV"][1] == 0.0

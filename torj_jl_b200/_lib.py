@@ -53,6 +53,8 @@ SIGNATURES = {
     "torj_bspline_prefilter_1d": (C.c_int, [C.c_int32, c_dp, c_dp]),
     "torj_plasma_create": (C.c_int, [c_vp, C.POINTER(TorjGrid), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int32,
                                      C.c_double, C.c_double, C.c_double, C.POINTER(c_vp)]),
+    "torj_plasma_create_from_data": (C.c_int, [c_vp, C.POINTER(TorjGrid), c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp, c_dp, c_dp,
+                                               c_dp, c_dp, C.c_int32, C.POINTER(c_vp)]),
     "torj_plasma_destroy": (None, [c_vp]),
     "torj_probe": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, c_dp, C.c_double, C.c_int32, c_dp]),
     "torj_rhs": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, C.c_double, C.c_int32, c_dp]),

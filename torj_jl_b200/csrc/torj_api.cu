@@ -296,6 +296,122 @@ int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, 
     return 0;
 }
 
+// natural cubic spline through (x, y), x strictly increasing, resampled on the uniform range x[0]..x[n-1] with n
+// points: IMAS.interp1d(x, y, :cubic).(range(x[1], x[end], length(x))) of reference src/plasma.jl:17-18,42-43
+static void resample_uniform(const double* x, const double* y, int n, std::vector<double>& xr, std::vector<double>& yr) {
+    std::vector<double> m2(n, 0.0);  // second derivatives, natural ends
+    if (n > 2) {
+        std::vector<double> cp(n), dp(n);
+        for (int i = 1; i < n - 1; ++i) {
+            double h0 = x[i] - x[i - 1], h1 = x[i + 1] - x[i];
+            double diag = 2.0 * (h0 + h1), rhs = 6.0 * ((y[i + 1] - y[i]) / h1 - (y[i] - y[i - 1]) / h0);
+            if (i == 1) { cp[i] = h1 / diag; dp[i] = rhs / diag; }
+            else { double den = diag - h0 * cp[i - 1]; cp[i] = h1 / den; dp[i] = (rhs - h0 * dp[i - 1]) / den; }
+        }
+        m2[n - 2] = dp[n - 2];
+        for (int i = n - 3; i >= 1; --i) m2[i] = dp[i] - cp[i] * m2[i + 1];
+    }
+    xr.resize(n); yr.resize(n);
+    int seg = 0;
+    for (int q = 0; q < n; ++q) {
+        double t = (q == n - 1) ? x[n - 1] : x[0] + (x[n - 1] - x[0]) * (double)q / (double)(n - 1);
+        xr[q] = t;
+        while (seg < n - 2 && t >= x[seg + 1]) ++seg;
+        double h = x[seg + 1] - x[seg], A = (x[seg + 1] - t) / h, B = (t - x[seg]) / h;
+        yr[q] = A * y[seg] + B * y[seg + 1] + ((A * A * A - A) * m2[seg] + (B * B * B - B) * m2[seg + 1]) * h * h / 6.0;
+    }
+}
+
+static std::vector<double> thomas_pivots(int n) {  // cp[k] of the (1/6, 2/3, 1/6) system with n-2 unknowns
+    std::vector<double> cp(std::max(n, 2));
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    cp[0] = a / b;
+    for (int k = 1; k < n; ++k) cp[k] = a / (b - a * cp[k - 1]);
+    return cp;
+}
+
+int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* psi_norm, const double* psi_prof,
+                                 const double* ne_prof, const double* Te_prof, int32_t n_prof, const double* BR,
+                                 const double* BZ, const double* Bphi, const double* psi_1d, const double* vol_1d,
+                                 int32_t n_1d, torj_plasma** out) {
+    if (!c || !g || !out) FAIL("torj_plasma_create_from_data: NULL argument");
+    if (g->nR < 2 || g->nZ < 2 || n_prof < 4 || n_1d < 2) FAIL("torj_plasma_create_from_data: grid or profile too small");
+    for (int i = 1; i < n_prof; ++i) if (!(psi_prof[i] > psi_prof[i - 1])) FAIL("torj_plasma_create_from_data: psi_prof must increase");
+    if (set_device(c)) return 1;
+    cudaStream_t st = c->stream;
+    const int nR = g->nR, nZ = g->nZ, sr = nR + 2;
+    const size_t npts = (size_t)nR * nZ, nodes = (size_t)sr * (nZ + 2);
+    // ---- 1-D host work (tiny): resample, log, prefilter (src/plasma.jl:16-19,42-44)
+    std::vector<double> xr, yr, c1[2];
+    double x0[2], hh[2];
+    const double* profs[2] = {ne_prof, Te_prof};
+    for (int q = 0; q < 2; ++q) {
+        resample_uniform(psi_prof, profs[q], n_prof, xr, yr);
+        for (auto& v : yr) v = std::log(v);
+        c1[q].resize(n_prof + 2);
+        prefilter_line(yr.data(), 1, n_prof, c1[q].data(), 1);
+        x0[q] = xr[0]; hh[q] = (xr[n_prof - 1] - xr[0]) / (double)(n_prof - 1);
+    }
+    std::vector<double> vr, vv, vc(n_1d + 2);
+    resample_uniform(psi_1d, vol_1d, n_1d, vr, vv);
+    prefilter_line(vv.data(), 1, n_1d, vc.data(), 1);
+    double psi_prof_max = psi_prof[0];
+    for (int i = 1; i < n_prof; ++i) psi_prof_max = std::max(psi_prof_max, psi_prof[i]);
+    // ---- device: node data of six fields, R pass, Z pass, pack
+    double *d_raw = nullptr, *d_tmp = nullptr, *d_coef = nullptr, *d_c1 = nullptr, *d_cpR = nullptr, *d_cpZ = nullptr;
+    CK(cudaMalloc(&d_raw, 6 * npts * sizeof(double)));
+    CK(cudaMalloc(&d_tmp, (size_t)sr * nZ * sizeof(double)));
+    CK(cudaMalloc(&d_coef, 6 * nodes * sizeof(double)));
+    CK(cudaMalloc(&d_c1, 2 * (size_t)(n_prof + 2) * sizeof(double)));
+    std::vector<double> cpR = thomas_pivots(nR), cpZ = thomas_pivots(nZ);
+    CK(cudaMalloc(&d_cpR, cpR.size() * sizeof(double)));
+    CK(cudaMalloc(&d_cpZ, cpZ.size() * sizeof(double)));
+    const double* src[6] = {psi_norm, nullptr, nullptr, BR, BZ, Bphi};  // field order: psi, lnne, lnTe, BR, BZ, Bphi
+    for (int f = 0; f < 6; ++f)
+        if (src[f]) CK(cudaMemcpyAsync(d_raw + f * npts, src[f], npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int q = 0; q < 2; ++q)
+        CK(cudaMemcpyAsync(d_c1 + q * (n_prof + 2), c1[q].data(), (n_prof + 2) * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cpR, cpR.data(), cpR.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cpZ, cpZ.data(), cpZ.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int q = 0; q < 2; ++q) {
+        k_profile_to_grid<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d_raw, (long long)npts, d_c1 + q * (n_prof + 2), n_prof,
+                                                                       x0[q], hh[q], d_raw + (1 + q) * npts);
+        c->launches++;
+    }
+    for (int f = 0; f < 6; ++f) {
+        // R pass: nZ lines of nR points (contiguous) -> tmp[(nR+2) x nZ]; Z pass: nR+2 columns of nZ points -> coef
+        k_prefilter_lines<<<(nZ + 127) / 128, 128, 0, st>>>(d_raw + f * npts, d_tmp, nR, nZ, nR, 1, sr, 1, d_cpR);
+        k_prefilter_lines<<<(sr + 127) / 128, 128, 0, st>>>(d_tmp, d_coef + f * nodes, nZ, sr, 1, sr, 1, sr, d_cpZ);
+        c->launches += 2;
+    }
+    CK(cudaGetLastError());
+    torj_plasma* p = new torj_plasma();
+    p->ctx = c;
+    p->id = ++g_plasma_serial;
+    CK(cudaMalloc(&p->dA, 2 * nodes * sizeof(double2)));
+    CK(cudaMalloc(&p->dB, nodes * sizeof(double2)));
+    k_pack_tables<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(d_coef, d_coef + nodes, d_coef + 2 * nodes, d_coef + 3 * nodes,
+                                                                 d_coef + 4 * nodes, d_coef + 5 * nodes, (long long)nodes, p->dA, p->dB);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_raw); cudaFree(d_tmp); cudaFree(d_coef); cudaFree(d_c1); cudaFree(d_cpR); cudaFree(d_cpZ);
+    DevTables& T = p->T;
+    T.A = p->dA; T.B = p->dB;
+    T.nR = nR; T.nZ = nZ; T.row = sr;
+    T.r0 = g->R_first; T.z0 = g->Z_first;
+    double hr = (g->R_last - g->R_first) / (double)(nR - 1), hz = (g->Z_last - g->Z_first) / (double)(nZ - 1);
+    T.inv_hr = 1.0 / hr; T.inv_hz = 1.0 / hz;
+    T.rlast = g->R_first + hr * (nR - 1); T.zlast = g->Z_first + hz * (nZ - 1);
+    T.psi_prof_max = psi_prof_max;
+    CK(cudaMalloc(&p->dT, sizeof(DevTables)));
+    CK(cudaMemcpy(p->dT, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
+    p->vol_c = vc;
+    p->n_vol = n_1d; p->vol_x0 = vr[0]; p->vol_h = (vr[n_1d - 1] - vr[0]) / (double)(n_1d - 1);
+    *out = p;
+    return 0;
+}
+
 void torj_plasma_destroy(torj_plasma* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);

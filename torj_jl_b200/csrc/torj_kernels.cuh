@@ -756,6 +756,77 @@ __global__ void k_dfma(int iters, double* out) {
     if (s == 12345.6789) out[0] = s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plasma construction on the device (reference src/plasma.jl:16-58): prefilter and table packing
+// ------------------------------------------------------------------------------------------------
+// One thread per line: natural-end cubic B-spline prefilter (rows 1/6, 2/3, 1/6; c[1] = y[0], c[n] = y[n-1]).
+// cp[k] are the data-independent Thomas pivots for this n. in/out are addressed with (line, element) strides so the
+// same kernel does the R pass (lines = Z rows) and the Z pass (lines = R columns of the intermediate array).
+__global__ void k_prefilter_lines(const double* __restrict__ in, double* __restrict__ out, int n, int n_lines,
+                                  long long in_ls, long long in_es, long long out_ls, long long out_es,
+                                  const double* __restrict__ cp) {
+    int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= n_lines) return;
+    const double* y = in + (long long)line * in_ls;
+    double* c = out + (long long)line * out_ls;
+    const double a = 1.0 / 6.0, b = 2.0 / 3.0;
+    const double s_first = y[0], s_last = y[(long long)(n - 1) * in_es];
+    const int m = n - 2;
+    // forward sweep; dp[k] is parked in c[k+2] (the slot of sol[k+1])
+    if (m >= 1) {
+        double prev = (y[in_es] - a * s_first - (m == 1 ? a * s_last : 0.0)) / b;
+        c[2 * out_es] = prev;
+        for (int k = 1; k < m; ++k) {
+            double r = y[(long long)(k + 1) * in_es];
+            if (k == m - 1) r -= a * s_last;
+            prev = (r - a * prev) / (b - a * cp[k - 1]);
+            c[(long long)(k + 2) * out_es] = prev;
+        }
+        // back substitution: sol[m] = dp[m-1]; sol[k+1] = dp[k] - cp[k] sol[k+2]
+        double nxt = c[(long long)(m + 1) * out_es];
+        for (int k = m - 2; k >= 0; --k) {
+            nxt = c[(long long)(k + 2) * out_es] - cp[k] * nxt;
+            c[(long long)(k + 2) * out_es] = nxt;
+        }
+    }
+    c[out_es] = s_first;
+    c[(long long)n * out_es] = s_last;
+    const double s1 = (n > 2) ? c[2 * out_es] : s_last;
+    const double sm2 = (n > 2) ? c[(long long)(n - 1) * out_es] : s_first;
+    c[0] = 2.0 * s_first - s1;
+    c[(long long)(n + 1) * out_es] = 2.0 * s_last - sm2;
+}
+
+// ln(profile) on the grid: 1-D cubic B-spline (uniform psi range, Line extrapolation) evaluated at every psi_N node
+// (reference src/plasma.jl:19-20)
+__global__ void k_profile_to_grid(const double* __restrict__ psi_nodes, long long n_nodes, const double* __restrict__ c1,
+                                  int n, double x0, double h, double* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double x = psi_nodes[i];
+    double xl = x0 + h * (n - 1);
+    double xc = fmin(fmax(x, x0), xl);
+    double u = (xc - x0) / h + 1.0;
+    int k = min(max((int)floor(u), 1), n - 1);
+    double d = u - (double)k, e = 1.0 - d;
+    double w0 = e * e * e / 6.0, w1 = 2.0 / 3.0 - d * d + d * d * d / 2.0, w2 = 2.0 / 3.0 - e * e + e * e * e / 2.0, w3 = d * d * d / 6.0;
+    double g0 = -e * e / 2.0 / h, g1 = (-2.0 * d + 1.5 * d * d) / h, g2 = (2.0 * e - 1.5 * e * e) / h, g3 = d * d / 2.0 / h;
+    const double* cc = c1 + (k - 1);
+    double v = w0 * cc[0] + w1 * cc[1] + w2 * cc[2] + w3 * cc[3];
+    double dv = g0 * cc[0] + g1 * cc[1] + g2 * cc[2] + g3 * cc[3];
+    out[i] = v + (x - xc) * dv;
+}
+
+// six coefficient tables -> the interleaved node layout of DevTables
+__global__ void k_pack_tables(const double* psi, const double* lnne, const double* lnTe, const double* BR, const double* BZ,
+                              const double* Bp, long long nodes, double2* A, double2* B) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nodes) return;
+    A[2 * k] = make_double2(BR[k], BZ[k]);
+    A[2 * k + 1] = make_double2(Bp[k], lnne[k]);
+    B[k] = make_double2(lnTe[k], psi[k]);
+}
+
 // dependent-issue latency of DFMA: one warp, one chain, cycles from clock64()
 __global__ void k_dfma_latency(int iters, double seed, double* out, long long* cycles) {
     double a = seed;

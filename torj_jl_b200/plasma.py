@@ -58,8 +58,15 @@ class Plasma:
     eqt1d_psi_norm, eqt1d_volume) — reference src/plasma.jl:30-32. 2-D arrays are [nR, nZ]."""
 
     def __init__(self, R_coords, Z_coords, psi_norm_data, psi_prof, ne_prof, Te_prof, Br_data, Bz_data, Bphi_data,
-                 eqt1d_psi_norm, eqt1d_volume):
+                 eqt1d_psi_norm, eqt1d_volume, *, build="host"):
+        """build="host": coefficient tables prefiltered on the host and uploaded (torj_plasma_create);
+        build="device": raw arrays uploaded, prefilter + packing run on the GPU (torj_plasma_create_from_data)."""
         f8 = lambda a: np.asarray(a, dtype=np.float64)
+        if build not in ("host", "device"):
+            raise ValueError("build must be 'host' or 'device'")
+        self.build = build
+        self._raw = dict(psi=f8(psi_norm_data), psi_prof=f8(psi_prof), ne=f8(ne_prof), Te=f8(Te_prof), BR=f8(Br_data),
+                         BZ=f8(Bz_data), Bphi=f8(Bphi_data), psi1d=f8(eqt1d_psi_norm), vol1d=f8(eqt1d_volume))
         self.R_coords, self.Z_coords = f8(R_coords), f8(Z_coords)
         psi_norm_data = f8(psi_norm_data)
         nR, nZ = len(self.R_coords), len(self.Z_coords)
@@ -99,10 +106,19 @@ class Plasma:
             g = _lib.TorjGrid(len(self.R_coords), len(self.Z_coords), self.R_coords[0], self.R_coords[-1],
                               self.Z_coords[0], self.Z_coords[-1])
             h = c_vp()
-            c = self.coefs
-            _lib.check(_lib.lib().torj_plasma_create(ctx, C.byref(g), _p(c["psi"]), _p(c["lnne"]), _p(c["lnTe"]), _p(c["BR"]),
-                                                     _p(c["BZ"]), _p(c["Bphi"]), _p(self.vol_coef), self.n_vol, self.vol_psi0,
-                                                     self.vol_dpsi, self.psi_prof_max, C.byref(h)))
+            if self.build == "device":
+                r = self._raw
+                t = lambda a: np.ascontiguousarray(a.T)  # [nR, nZ] -> R fastest
+                keep = [t(r["psi"]), t(r["BR"]), t(r["BZ"]), t(r["Bphi"])]
+                _lib.check(_lib.lib().torj_plasma_create_from_data(
+                    ctx, C.byref(g), _p(keep[0]), _p(np.ascontiguousarray(r["psi_prof"])), _p(np.ascontiguousarray(r["ne"])),
+                    _p(np.ascontiguousarray(r["Te"])), len(r["psi_prof"]), _p(keep[1]), _p(keep[2]), _p(keep[3]),
+                    _p(np.ascontiguousarray(r["psi1d"])), _p(np.ascontiguousarray(r["vol1d"])), len(r["psi1d"]), C.byref(h)))
+            else:
+                c = self.coefs
+                _lib.check(_lib.lib().torj_plasma_create(ctx, C.byref(g), _p(c["psi"]), _p(c["lnne"]), _p(c["lnTe"]), _p(c["BR"]),
+                                                         _p(c["BZ"]), _p(c["Bphi"]), _p(self.vol_coef), self.n_vol, self.vol_psi0,
+                                                         self.vol_dpsi, self.psi_prof_max, C.byref(h)))
             self._handles[key] = h
         return self._handles[key]
 
