@@ -274,9 +274,11 @@ def main():
         # k_ray_init and k_finalize are < 1 % of the step (profiles/), so the step time stands for the kernel.
         tf, tms = C.c_double(), C.c_double()
         _lib.check(L.torj_fp64_peak(ctx, 20000, C.byref(tf), C.byref(tms)))
+        kms = C.c_double()
+        _lib.check(L.torj_ctx_last_trace_ms(ctx, C.byref(kms)))  # k_trace alone, CUDA events on its own stream
         achieved = algorithmic_flops(c) / (ms_per_step * 1e-3) / 1e12
         roof = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-                "traffic": ncu_traffic(), "kernel": "k_trace<Tsit5>",
+                "traffic": ncu_traffic(), "kernel": "k_trace<Tsit5>", "kernel_ms_last_launch": kms.value,
                 "peak_source": "DFMA-chain microbenchmark torj_fp64_peak measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_launch": algorithmic_flops(c), "counters": c}
         line = {"metric": "ray-steps/s", "value": steps_all / (ms_per_step * 1e-3), "unit": "ray-steps/s", "n_gpus": world,
