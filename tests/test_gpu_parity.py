@@ -378,6 +378,52 @@ def test_config3_full_size_properties(gpu_full, oracle_full, gl24, launcher):
     assert l2rel(sub["dP_dV"], ref["dP_dV"]) < L2_LIKE
 
 
+def test_config4_angle_sweep_properties(gpu_full, oracle_full, gl24):
+    """BASELINE.json configs[3] geometry at reduced count: 8 x 8 launcher angles x 1 025-ray beams = 65 600 rays in one call,
+    one profile per beam; per-beam identities of reference test/tests/test_make_beam.jl:14-21 and an oracle spot check."""
+    psi = np.linspace(0, 1, 400)
+    Ls = []
+    for pol in np.deg2rad(np.linspace(10.0, 40.0, 8)):
+        for tor in np.deg2rad(np.linspace(-15.0, 15.0, 8)):
+            Ls.append(dict(r=2.5, phi=0.0, z=0.4, steering_angle_pol=pol, steering_angle_tor=tor, spot_size=0.0174,
+                           inverse_curvature_radius=1 / 3.99, f=95e9, mode=1))
+    dP, dep, W, Pf, res = tj.make_beams(gpu_full, Ls, 1.0, psi, N_rings=7, min_azimuthal_points=20)
+    assert dP.shape == (64, 400) and len(res["status"]) == 64 * 1025
+    ok = res["status"] == 0
+    assert ok.mean() > 0.999
+    off = np.cumsum([0] + [len(w) for w in W])
+    for b in range(64):
+        sl = slice(off[b], off[b + 1])
+        okb = ok[sl]
+        absorbed = float(np.sum(W[b][okb] * (1.0 - Pf[b][okb])))
+        assert abs(dep[b] - absorbed) < 1e-3                       # profile-integrated power == 1 - sum w P_end
+        assert abs(float(np.sum(W[b][okb] * res["P_deposited_ray"][sl][okb])) - dep[b]) < 1e-12
+    # the whole-bundle counters are the sums of the per-ray ones
+    assert res["counters"]["n_acc"] == int(np.sum(np.maximum(res["n_points"] - 2, 0)))
+    # oracle spot check: three beams, 12 rays each
+    for b in (0, 27, 63):
+        L = Ls[b]
+        N0 = tj.pol_tor_angles_2_vector(L["steering_angle_pol"], L["steering_angle_tor"])
+        pos, dirs, w = tj.launch_peripheral_rays(np.array([2.5, 0.0, 0.4]), N0, 0.0174, 1 / 3.99, 95e9, N_rings=7, min_azimuthal_points=20)
+        pick = np.linspace(0, len(w) - 1, 12).astype(int)
+        ref = oracle_full.trace_bundle(pos[pick], dirs[pick], w[pick], 95e9, 1, 1.0, psi, gl24, deposition="streaming")
+        good = ref["status"] == 0
+        assert np.array_equal(res["status"][off[b] + pick] == 0, good)
+        assert np.array_equal(res["n_points"][off[b] + pick][good], ref["n_points"][good])
+        assert np.abs(Pf[b][pick][good] - ref["P_final"][good]).max() < 1e-11
+
+
+def test_measurement_helpers():
+    import ctypes as C
+    from torj_jl_b200 import _lib
+    ctx = _lib.context()
+    lat, ms = C.c_double(), C.c_double()
+    _lib.check(tj.lib().torj_fp64_latency(ctx, 2000, C.byref(lat)))
+    assert 4.0 < lat.value < 16.0                                   # measured 8.2 cycles on B200
+    _lib.check(tj.lib().torj_ctx_last_trace_ms(ctx, C.byref(ms)))    # earlier tests in this module have traced
+    assert ms.value > 0.0
+
+
 def test_fp64_peak_probe_and_launch_counter():
     import ctypes as C
     from torj_jl_b200 import _lib
