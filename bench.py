@@ -161,9 +161,6 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.warmup < 3 and not args.small:
-        args.warmup = max(args.warmup, 0)
-
     import torch
     import torch.distributed as dist
     import torj_jl_b200 as tj
