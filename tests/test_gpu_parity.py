@@ -323,6 +323,31 @@ def test_device_side_plasma_construction(arrays_small, oracle_small, gl24, launc
     assert abs(rb["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
 
 
+def test_config5_high_te_third_harmonic_scan(gl24):
+    """BASELINE.json configs[4] geometry with the Albajar model (the warm-plasma file of the reference is dead code,
+    DESIGN.md §7): launchers at z = +-0.4, 110 and 170 GHz, T_e0 = 25 keV, one profile per beam in one call.
+    170 GHz is absorbed at the THIRD harmonic (larger Bessel arguments, m = 3 dominant)."""
+    tj.abs_Al_init(24)
+    arr = tj.solovev_arrays(129, 129, Te0=25e3)
+    pl = tj.Plasma(*arr.values()); opl = O.OraclePlasma(*arr.values())
+    psi = np.linspace(0, 1, 200)
+    Ls = [dict(r=2.5, phi=0.0, z=z0, steering_angle_pol=np.deg2rad(pol), steering_angle_tor=0.1, spot_size=0.0174,
+               inverse_curvature_radius=1 / 3.99, f=f, mode=1)
+          for f in (110e9, 170e9) for z0, pol in ((0.4, 30.0), (-0.4, -30.0))]
+    dP, dep, W, Pf, res = tj.make_beams(pl, Ls, 1.0, psi, N_rings=2, min_azimuthal_points=3)
+    assert (res["status"] == 0).all() and dP.shape == (4, 200)
+    assert res["counters"]["n_harm"] > 0
+    for b, L in enumerate(Ls):
+        x0 = np.array([L["r"], 0.0, L["z"]])
+        N0 = tj.pol_tor_angles_2_vector(L["steering_angle_pol"], L["steering_angle_tor"])
+        pos, dirs, w = tj.launch_peripheral_rays(x0, N0, 0.0174, 1 / 3.99, L["f"], N_rings=2, min_azimuthal_points=3)
+        ref = opl.trace_bundle(pos, dirs, w, L["f"], 1, 1.0, psi, gl24)
+        assert np.abs(Pf[b] - ref["P_final"]).max() < 1e-10
+        assert abs(dep[b] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+        assert l2rel(dP[b], ref["dP_dV"]) < L2_FAITHFUL
+    assert dep[2] > 0.99 and Pf[2].max() > 1e-5           # 170 GHz: strong but incomplete third-harmonic absorption
+
+
 def test_smallest_inputs(gpu_small, launcher):
     r = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 1.0]))
     assert r["status"][0] == 0 and r["dP_dV"].shape == (2,) and r["dP_dV"][1] == 0.0
