@@ -13,6 +13,8 @@
  *   - 2-D tables are "R fastest" (a Julia Matrix[nR+2, nZ+2] passed as is); ray positions/directions are
  *     component-major [3][n] (a Julia Matrix[n,3] passed as is, reference src/launch.jl:84-85).
  *   - all arithmetic is FP64.  There is no CPU fallback: without a CUDA device torj_ctx_create fails.
+ *   - calls are blocking unless stated otherwise; a torj_ctx (and the objects created on it) must not be used from two
+ *     threads at once — use one context per host thread / per GPU.
  */
 #ifndef TORJ_CUDA_H
 #define TORJ_CUDA_H
