@@ -116,11 +116,12 @@ def cpu_baseline(rank_bundle, seconds_target=15.0):
     n_sample = int(max(cores * 2, min(len(w), round(seconds_target * cores / 0.3))))
     pick = np.linspace(0, len(w) - 1, n_sample).astype(int)
     t0 = time.perf_counter()
+    # the reference's own deposition algorithm (spline roots per psi level, src/plasma.jl:91-151; psi(s) fitted once)
     r = opl.trace_bundle(pos[pick], dirs[pick], w[pick], WORKLOAD["f"], WORKLOAD["mode"], WORKLOAD["s_max"], psi, gl,
-                         deposition="streaming", n_threads=cores)
+                         deposition="faithful", n_threads=cores)
     dt = time.perf_counter() - t0
     return dict(value=r["counters"]["n_acc"] / dt, unit="ray-steps/s", cores=cores, kind="port",
-                sample=f"{n_sample} of {len(w)} rays of the same bundle, evenly spaced, streaming deposition, {dt:.1f} s",
+                sample=f"{n_sample} of {len(w)} rays of the same bundle, evenly spaced, reference deposition algorithm, {dt:.1f} s",
                 rays_per_s=n_sample / dt, seconds=dt, n_rays=n_sample, steps=int(r["counters"]["n_acc"]))
 
 
