@@ -120,7 +120,12 @@ def cpu_baseline(rank_bundle, seconds_target=15.0):
     r = opl.trace_bundle(pos[pick], dirs[pick], w[pick], WORKLOAD["f"], WORKLOAD["mode"], WORKLOAD["s_max"], psi, gl,
                          deposition="faithful", n_threads=cores)
     dt = time.perf_counter() - t0
-    return dict(value=r["counters"]["n_acc"] / dt, unit="ray-steps/s", cores=cores, kind="port",
+    t1 = time.perf_counter()
+    opl.trace_bundle(pos[pick[::4]], dirs[pick[::4]], w[pick[::4]], WORKLOAD["f"], WORKLOAD["mode"], WORKLOAD["s_max"], psi, gl,
+                     deposition="streaming", n_threads=cores)
+    dt_s = (time.perf_counter() - t1) * 4.0  # quarter sample, scaled: the GPU's deposition algorithm on the CPU
+    return dict(value=r["counters"]["n_acc"] / dt, value_streaming_deposition=r["counters"]["n_acc"] / dt_s,
+                unit="ray-steps/s", cores=cores, kind="port",
                 sample=f"{n_sample} of {len(w)} rays of the same bundle, evenly spaced, reference deposition algorithm, {dt:.1f} s",
                 rays_per_s=n_sample / dt, seconds=dt, n_rays=n_sample, steps=int(r["counters"]["n_acc"]))
 
@@ -294,7 +299,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                 "absorbed_fraction": dep.value / max(1, world) if world > 1 else dep.value}
         if not args.no_cpu_baseline and world >= 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline((pos, dirs, w)).items() if k in ("value", "unit", "cores", "kind", "sample", "rays_per_s")}
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline((pos, dirs, w)).items() if k in ("value", "value_streaming_deposition", "unit", "cores", "kind", "sample", "rays_per_s")}
         print(json.dumps(line), flush=True)
     L.torj_bundle_destroy(bh)
     if world > 1:
