@@ -162,6 +162,29 @@ int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int
                /* optional trajectories */ int64_t traj_first, int64_t traj_count, int32_t traj_max_pts, double* traj_s,
                double* traj_xyz, double* traj_P, double* traj_dP_ds, double* traj_dP_dV_ray, torj_counters* counters);
 
+/* --- single-process multi-GPU front end ----------------------------------------------------------------------- */
+/* For a host that is ONE process on a multi-GPU box (a Julia session calling make_beam): the same call as torj_trace,
+ * sharded by contiguous ray blocks over the devices (one host thread and one context per device, tables replicated),
+ * with the weighted sum of reference src/solve.jl:233-240 done on the host in device order — bit-reproducible for a
+ * given device count. (bench.py uses one process per GPU and an NCCL all-reduce instead.) */
+typedef struct torj_multi torj_multi;
+typedef struct torj_mplasma torj_mplasma;
+int torj_multi_create(int32_t n_devices /* <= 0: all visible */, torj_multi** out);
+void torj_multi_destroy(torj_multi* m);
+int32_t torj_multi_device_count(const torj_multi* m);
+int torj_multi_abs_init(torj_multi* m, int32_t n, const double* nodes, const double* weights);
+int torj_multi_plasma_create_from_data(torj_multi* m, const torj_grid* grid, const double* psi_norm, const double* psi_prof,
+                                       const double* ne_prof, const double* Te_prof, int32_t n_prof, const double* BR,
+                                       const double* BZ, const double* Bphi, const double* psi_1d, const double* vol_1d,
+                                       int32_t n_1d, torj_mplasma** out);
+void torj_multi_plasma_destroy(torj_mplasma* mp);
+int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* opt, int64_t n_rays, const double* pos,
+                     const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
+                     double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id,
+                     double* dP_dV, double* deposited_power, double* P_final, double* P_deposited_ray, int32_t* n_points,
+                     int32_t* status, int64_t traj_first, int64_t traj_count, int32_t traj_max_pts, double* traj_s,
+                     double* traj_xyz, double* traj_P, double* traj_dP_ds, double* traj_dP_dV_ray, torj_counters* counters);
+
 /* --- measurement ------------------------------------------------------------------------------------------- */
 /* Register-resident DFMA-chain microbenchmark: the FP64 roofline denominator (MEASURED_PEAKS.json has none). */
 int torj_fp64_peak(torj_ctx* ctx, int32_t iters, double* tflops, double* ms);

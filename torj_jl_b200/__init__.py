@@ -6,6 +6,7 @@ libtorj_cuda.so (hand-written sm_100a CUDA, C ABI in include/torj_cuda.h); there
 from ._lib import TorjError, TorjOptions, context, default_options, lib  # noqa: F401
 from .absorption import abs_Al_init, alpha_approx  # noqa: F401
 from .launch import launch_peripheral_rays  # noqa: F401
+from .multi import MultiGPU  # noqa: F401
 from .plasma import Plasma, evaluate_psi  # noqa: F401
 from .solve import make_beam, make_beams, make_ray, trace_bundle  # noqa: F401
 from .synthetic import pol_tor_angles_2_vector, solovev_arrays  # noqa: F401

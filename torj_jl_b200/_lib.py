@@ -69,6 +69,16 @@ SIGNATURES = {
     "torj_trace": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int32,
                              C.c_double, C.c_int32, c_dp, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip, C.c_int64, C.c_int64,
                              C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TorjCounters)]),
+    "torj_multi_create": (C.c_int, [C.c_int32, C.POINTER(c_vp)]),
+    "torj_multi_destroy": (None, [c_vp]),
+    "torj_multi_device_count": (C.c_int32, [c_vp]),
+    "torj_multi_abs_init": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
+    "torj_multi_plasma_create_from_data": (C.c_int, [c_vp, C.POINTER(TorjGrid), c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp, c_dp,
+                                                     c_dp, c_dp, c_dp, C.c_int32, C.POINTER(c_vp)]),
+    "torj_multi_plasma_destroy": (None, [c_vp]),
+    "torj_multi_trace": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int32,
+                                   C.c_double, C.c_int32, c_dp, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip, C.c_int64,
+                                   C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TorjCounters)]),
     "torj_fp64_peak": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
     "torj_fp64_latency": (C.c_int, [c_vp, C.c_int32, c_dp]),
 }

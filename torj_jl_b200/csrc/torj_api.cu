@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/torj_cuda.h"
@@ -762,6 +763,130 @@ int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
         c->ws = nullptr;
     }
     return rc;
+}
+
+// ---- single-process multi-GPU front end (what a Julia make_beam on an 8-GPU box calls) -------------------------
+struct torj_multi {
+    std::vector<torj_ctx*> ctx;
+};
+struct torj_mplasma {
+    std::vector<torj_plasma*> p;
+};
+
+int torj_multi_create(int32_t n_devices, torj_multi** out) {
+    if (!out) FAIL("torj_multi_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_err = std::string("torj_multi_create: no CUDA device (") + cudaGetErrorString(e) + "); libtorj_cuda has no CPU path";
+        return 1;
+    }
+    if (n_devices <= 0 || n_devices > ndev) n_devices = ndev;
+    torj_multi* m = new torj_multi();
+    for (int d = 0; d < n_devices; ++d) {
+        torj_ctx* c = nullptr;
+        if (torj_ctx_create(d, nullptr, &c)) { for (auto* q : m->ctx) torj_ctx_destroy(q); delete m; return 1; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return 0;
+}
+
+void torj_multi_destroy(torj_multi* m) {
+    if (!m) return;
+    for (auto* c : m->ctx) torj_ctx_destroy(c);
+    delete m;
+}
+
+int32_t torj_multi_device_count(const torj_multi* m) { return (int32_t)m->ctx.size(); }
+
+int torj_multi_abs_init(torj_multi* m, int32_t n, const double* nodes, const double* weights) {
+    for (auto* c : m->ctx)
+        if (int rc = torj_abs_init(c, n, nodes, weights)) return rc;
+    return 0;
+}
+
+int torj_multi_plasma_create_from_data(torj_multi* m, const torj_grid* g, const double* psi_norm, const double* psi_prof,
+                                       const double* ne_prof, const double* Te_prof, int32_t n_prof, const double* BR,
+                                       const double* BZ, const double* Bphi, const double* psi_1d, const double* vol_1d,
+                                       int32_t n_1d, torj_mplasma** out) {
+    if (!out) FAIL("torj_multi_plasma_create_from_data: out is NULL");
+    torj_mplasma* mp = new torj_mplasma();
+    for (auto* c : m->ctx) {  // the tables (3.2 MB for 257x257) are replicated on every device
+        torj_plasma* p = nullptr;
+        int rc = torj_plasma_create_from_data(c, g, psi_norm, psi_prof, ne_prof, Te_prof, n_prof, BR, BZ, Bphi, psi_1d, vol_1d,
+                                              n_1d, &p);
+        if (rc) { for (auto* q : mp->p) torj_plasma_destroy(q); delete mp; return rc; }
+        mp->p.push_back(p);
+    }
+    *out = mp;
+    return 0;
+}
+
+void torj_multi_plasma_destroy(torj_mplasma* mp) {
+    if (!mp) return;
+    for (auto* p : mp->p) torj_plasma_destroy(p);
+    delete mp;
+}
+
+// Rays are split into contiguous blocks, one per device, traced concurrently by one host thread per device; profiles
+// and deposited power are summed on the host in device order (deterministic), per-ray outputs land in their slices.
+int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* opt, int64_t n_rays, const double* pos,
+                     const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
+                     double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id,
+                     double* dP_dV, double* deposited_power, double* P_final, double* P_dep, int32_t* n_points,
+                     int32_t* status, int64_t traj_first, int64_t traj_count, int32_t traj_max_pts, double* traj_s,
+                     double* traj_xyz, double* traj_P, double* traj_dP_ds, double* traj_dP_dV_ray, torj_counters* counters) {
+    const int nd = (int)m->ctx.size();
+    if ((int)mp->p.size() != nd) FAIL("torj_multi_trace: plasma was created on a different device set");
+    if (n_rays < 1) FAIL("torj_multi_trace: n_rays < 1");
+    if (n_beams < 1 || !beam_id) n_beams = 1;
+    const int used = (int)std::min<int64_t>(nd, n_rays);
+    std::vector<int> rcs(used, 0);
+    std::vector<std::string> errs(used);
+    std::vector<std::vector<double>> prof(used), dep(used);
+    std::vector<torj_counters> cnts(used);
+    std::vector<std::thread> th;
+    const int64_t base = n_rays / used, rem = n_rays % used;
+    for (int d = 0; d < used; ++d) {
+        th.emplace_back([&, d]() {
+            const int64_t lo = d * base + std::min<int64_t>(d, rem), n = base + (d < rem ? 1 : 0);
+            std::vector<double> p3(3 * n), d3(3 * n);
+            for (int c = 0; c < 3; ++c) {
+                memcpy(p3.data() + c * n, pos + c * n_rays + lo, n * sizeof(double));
+                memcpy(d3.data() + c * n, dir + c * n_rays + lo, n * sizeof(double));
+            }
+            prof[d].assign((size_t)n_beams * n_psi, 0.0);
+            dep[d].assign(n_beams, 0.0);
+            // the part of the trajectory window that falls into this block
+            int64_t w0 = std::max(traj_first, lo), w1 = std::min(traj_first + traj_count, lo + n);
+            int64_t wc = std::max<int64_t>(0, w1 - w0), wo = w0 - traj_first;
+            auto off = [&](double* b, size_t row) { return (b && wc > 0) ? b + (size_t)wo * row : nullptr; };
+            memset(&cnts[d], 0, sizeof(torj_counters));
+            rcs[d] = torj_trace(m->ctx[d], mp->p[d], opt, n, p3.data(), d3.data(), weight + lo,
+                                per_ray_fm ? freq_hz + lo : freq_hz, per_ray_fm ? mode + lo : mode, per_ray_fm, s_max, n_psi,
+                                psi_edges, n_beams, (n_beams > 1) ? beam_id + lo : nullptr, prof[d].data(), dep[d].data(),
+                                P_final ? P_final + lo : nullptr, P_dep ? P_dep + lo : nullptr, n_points ? n_points + lo : nullptr,
+                                status ? status + lo : nullptr, wc > 0 ? w0 - lo : 0, wc, traj_max_pts,
+                                off(traj_s, traj_max_pts), off(traj_xyz, 3 * (size_t)traj_max_pts), off(traj_P, traj_max_pts),
+                                off(traj_dP_ds, traj_max_pts), off(traj_dP_dV_ray, n_psi), &cnts[d]);
+            if (rcs[d]) errs[d] = g_err;  // g_err is thread-local
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < used; ++d)
+        if (rcs[d]) { g_err = "device " + std::to_string(d) + ": " + errs[d]; return rcs[d]; }
+    if (dP_dV) for (size_t k = 0; k < (size_t)n_beams * n_psi; ++k) { double s = 0.0; for (int d = 0; d < used; ++d) s += prof[d][k]; dP_dV[k] = s; }
+    if (deposited_power) for (int b = 0; b < n_beams; ++b) { double s = 0.0; for (int d = 0; d < used; ++d) s += dep[d][b]; deposited_power[b] = s; }
+    if (counters) {
+        memset(counters, 0, sizeof(torj_counters));
+        for (int d = 0; d < used; ++d) {
+            counters->n_acc += cnts[d].n_acc; counters->n_rej += cnts[d].n_rej; counters->n_rhs += cnts[d].n_rhs;
+            counters->n_alpha += cnts[d].n_alpha; counters->n_harm += cnts[d].n_harm; counters->n_rays_ok += cnts[d].n_rays_ok;
+            counters->n_harm_pruned += cnts[d].n_harm_pruned; counters->n_alpha_skipped += cnts[d].n_alpha_skipped;
+        }
+    }
+    return 0;
 }
 
 int torj_fp64_peak(torj_ctx* c, int32_t iters, double* tflops, double* ms) {
