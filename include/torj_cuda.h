@@ -130,6 +130,16 @@ int torj_rhs(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64
 /* freq_hz/mode: per ray when per_ray_fm != 0, else length 1. */
 int torj_bundle_create(torj_ctx* ctx, int64_t n_rays, const double* pos, const double* dir, const double* weight,
                        const double* freq_hz, const int32_t* mode, int32_t per_ray_fm, torj_bundle** out);
+/* launch_peripheral_rays (reference src/launch.jl:24-132) for n_launchers beams at once, on the device: launcher
+ * parameters x0/N0 [3][nl], w, inv_Rc, f, mode [nl]; common N_rings / min_azimuthal_points / normalize_weight_sum;
+ * gh_nodes/gh_weights = Gauss-Hermite rule of order 2*N_rings+2 (ascending nodes). Ray k of launcher L is ray
+ * L*n_per+k; the bundle carries per-ray frequency/mode and one deposition profile per launcher (n_beams = nl). */
+int torj_bundle_create_from_launchers(torj_ctx* ctx, int32_t n_launchers, const double* x0, const double* N0, const double* w,
+                                      const double* inv_Rc, const double* f, const int32_t* mode, int32_t N_rings,
+                                      int32_t min_azimuthal_points, int32_t normalize_weight_sum, const double* gh_nodes,
+                                      const double* gh_weights, torj_bundle** out, int64_t* n_rays_out);
+/* launch arrays of a bundle back to the host: pos/dir [3][n], weight [n]; any pointer may be NULL */
+int torj_bundle_rays(torj_bundle* b, double* pos, double* dir, double* weight);
 void torj_bundle_destroy(torj_bundle* b);
 /* Trajectories are kept for rays [traj_first, traj_first+traj_count), up to traj_max_pts points each. */
 int torj_bundle_set_window(torj_bundle* b, int64_t traj_first, int64_t traj_count, int32_t traj_max_pts);

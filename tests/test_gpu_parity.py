@@ -438,6 +438,30 @@ def test_config4_angle_sweep_properties(gpu_full, oracle_full, gl24):
         assert np.abs(Pf[b][pick][good] - ref["P_final"][good]).max() < 1e-11
 
 
+def test_device_side_ray_generation(gpu_small, launcher):
+    """torj_bundle_create_from_launchers == launch_peripheral_rays (reference src/launch.jl:24-132) per launcher,
+    divergent / convergent / paraxial beams, with and without weight normalisation."""
+    import ctypes as C
+    from torj_jl_b200 import _lib
+    base = dict(r=2.5, phi=0.0, z=0.4, spot_size=launcher["spot"], f=95e9, mode=1)
+    Ls = [dict(base, steering_angle_pol=np.deg2rad(30.0), steering_angle_tor=0.0, inverse_curvature_radius=launcher["inv_Rc"]),
+          dict(base, steering_angle_pol=np.deg2rad(22.0), steering_angle_tor=0.2, inverse_curvature_radius=-1 / 2.5, f=110e9, mode=-1),
+          dict(base, steering_angle_pol=np.deg2rad(35.0), steering_angle_tor=-0.1, inverse_curvature_radius=np.inf, spot_size=0.03, phi=0.3)]
+    psi = np.linspace(0, 1, 90)
+    for norm in (True, False):
+        kw = dict(N_rings=4, min_azimuthal_points=7, normalize_weight_sum=norm)
+        a = tj.make_beams(gpu_small, Ls, 0.4, psi, **kw)
+        b = tj.make_beams(gpu_small, Ls, 0.4, psi, device_launch=True, **kw)
+        for q in range(3):
+            assert np.abs(a[2][q] - b[2][q]).max() <= 1e-14 * a[2][q].max()            # ray weights
+            assert np.array_equal(a[4]["n_points"], b[4]["n_points"])
+            assert np.abs(a[3][q] - b[3][q]).max() < 1e-10                             # P_final per ray
+            assert np.abs(a[0][q] - b[0][q]).max() <= 1e-9 * max(np.abs(a[0][q]).max(), 1e-300)
+        assert np.abs(a[1] - b[1]).max() < 1e-10
+    with pytest.raises((ValueError, tj.TorjError)):
+        tj.make_beams(gpu_small, Ls, 0.4, psi, device_launch=True, N_rings=1)
+
+
 def test_single_process_multi_gpu_front_end(gpu_small, arrays_small, launcher):
     """torj_multi_trace: shards over all visible GPUs in one process (1 GPU here at round end, N under gpurun --gpus N);
     the host-side ordered sum reproduces the single-device result."""

@@ -59,6 +59,9 @@ SIGNATURES = {
     "torj_probe": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, c_dp, C.c_double, C.c_int32, c_dp]),
     "torj_rhs": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, C.c_double, C.c_int32, c_dp]),
     "torj_bundle_create": (C.c_int, [c_vp, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int32, C.POINTER(c_vp)]),
+    "torj_bundle_create_from_launchers": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int32, C.c_int32,
+                                                    C.c_int32, c_dp, c_dp, C.POINTER(c_vp), C.POINTER(C.c_int64)]),
+    "torj_bundle_rays": (C.c_int, [c_vp, c_dp, c_dp, c_dp]),
     "torj_bundle_destroy": (None, [c_vp]),
     "torj_bundle_set_window": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32]),
     "torj_bundle_set_beams": (C.c_int, [c_vp, C.c_int32, c_ip]),

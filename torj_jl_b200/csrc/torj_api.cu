@@ -541,6 +541,101 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     return 0;
 }
 
+// Bundle generated on the device from launcher parameters: launch_peripheral_rays (reference src/launch.jl:24-132) for
+// n_launchers beams at once; ray k of launcher L is ray L*n_per+k, its beam index is L, frequency and mode are per ray.
+// gh_nodes/gh_weights: Gauss-Hermite rule of order 2*N_rings+2 (FastGaussQuadrature.gausshermite, src/launch.jl:72).
+int torj_bundle_create_from_launchers(torj_ctx* c, int32_t n_launchers, const double* x0, const double* N0, const double* w,
+                                      const double* inv_Rc, const double* f, const int32_t* mode, int32_t N_rings,
+                                      int32_t min_azimuthal_points, int32_t normalize_weight_sum, const double* gh_nodes,
+                                      const double* gh_weights, torj_bundle** out, int64_t* n_rays_out) {
+    if (!c || !out || n_launchers < 1) FAIL("torj_bundle_create_from_launchers: bad argument");
+    if (N_rings < 2) FAIL("N_rings < 2 which is the minimum");  // ArgumentError of src/launch.jl:27-29
+    if (set_device(c)) return 1;
+    // ring radii in units of w/sqrt(2): v[N_rings+2:end] of the ascending rule, first N_rings used (src/launch.jl:72-83)
+    std::vector<double> ru(N_rings), rwu(N_rings);
+    std::vector<int> start(N_rings + 1, 0);
+    double wsum = 0.0;
+    for (int i = 0; i < N_rings; ++i) {
+        ru[i] = gh_nodes[N_rings + 1 + i];
+        rwu[i] = gh_weights[N_rings + 1 + i];
+        long nth = std::max(1L, (long)std::nearbyint((double)min_azimuthal_points * ru[i] / ru[0]));
+        start[i + 1] = start[i] + (int)nth;
+    }
+    // sum of the launcher's weights, accumulated ray by ray in launch order like `sum(ray_weights)` does
+    for (int i = 0; i < N_rings; ++i) {
+        int nth = start[i + 1] - start[i];
+        double wt = ru[i] * rwu[i] * (2.0 * M_PI / (double)nth);
+        for (int j = 0; j < nth; ++j) wsum += wt;
+    }
+    const int n_per = start[N_rings];
+    const int64_t n = (int64_t)n_launchers * n_per;
+    // an empty bundle shell with device arrays, then the generator kernel fills pos/dir/weight/freq/mode/beam
+    std::vector<double> zero3(3, 0.0);
+    torj_bundle* b = new torj_bundle();
+    b->ctx = c; b->n = n; b->per_ray_fm = 1;
+    CK(cudaMalloc(&b->d_pos, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_dir, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_w, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_freq, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_mode, n * sizeof(int)));
+    CK(cudaMalloc(&b->d_u0, 7 * n * sizeof(double)));
+    CK(cudaMalloc(&b->d_s0, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_psil, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_Pf, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_Pdep, n * sizeof(double)));
+    CK(cudaMalloc(&b->d_status, n * sizeof(int)));
+    CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
+    CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_beam, n * sizeof(int)));
+    b->n_beams = n_launchers;
+    BundleDev& B = b->B;
+    B.n_rays = n; B.pos = b->d_pos; B.dir = b->d_dir; B.weight = b->d_w; B.freq = b->d_freq; B.mode = b->d_mode;
+    B.per_ray_fm = 1; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
+    B.P_final = b->d_Pf; B.P_dep = b->d_Pdep; B.n_points = b->d_npts;
+    // launcher parameters to the device
+    const size_t nl = n_launchers;
+    double* d_par = nullptr; int* d_ipar = nullptr;
+    CK(cudaMalloc(&d_par, (9 * nl + 2 * N_rings) * sizeof(double)));
+    CK(cudaMalloc(&d_ipar, (nl + N_rings + 1) * sizeof(int)));
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(d_par, x0, 3 * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 3 * nl, N0, 3 * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 6 * nl, w, nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 7 * nl, inv_Rc, nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 8 * nl, f, nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 9 * nl, ru.data(), N_rings * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_par + 9 * nl + N_rings, rwu.data(), N_rings * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ipar, mode, nl * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ipar + nl, start.data(), (N_rings + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    LaunchArgs A;
+    A.n_launchers = n_launchers; A.n_rings = N_rings; A.n_per = n_per;
+    A.x0 = d_par; A.N0 = d_par + 3 * nl; A.w = d_par + 6 * nl; A.inv_Rc = d_par + 7 * nl; A.f = d_par + 8 * nl;
+    A.r_unit = d_par + 9 * nl; A.rw_unit = d_par + 9 * nl + N_rings;
+    A.mode = d_ipar; A.ring_start = d_ipar + nl;
+    A.wsum_unit = wsum; A.normalize = normalize_weight_sum;
+    A.pos = b->d_pos; A.dir = b->d_dir; A.weight = b->d_w; A.freq = b->d_freq; A.mode_out = b->d_mode; A.beam = b->d_beam;
+    k_launch_rays<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_par); cudaFree(d_ipar);
+    *out = b;
+    if (n_rays_out) *n_rays_out = n;
+    return 0;
+}
+
+// copy the generated (or uploaded) launch arrays back: pos/dir [3][n], weight [n] (any pointer may be NULL)
+int torj_bundle_rays(torj_bundle* b, double* pos, double* dir, double* weight) {
+    torj_ctx* c = b->ctx;
+    if (set_device(c)) return 1;
+    if (pos) CK(cudaMemcpyAsync(pos, b->d_pos, 3 * b->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (dir) CK(cudaMemcpyAsync(dir, b->d_dir, 3 * b->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (weight) CK(cudaMemcpyAsync(weight, b->d_w, b->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 void torj_bundle_destroy(torj_bundle* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);

@@ -827,6 +827,80 @@ __global__ void k_pack_tables(const double* psi, const double* lnne, const doubl
     B[k] = make_double2(lnTe[k], psi[k]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// launch_peripheral_rays for many launchers at once (reference src/launch.jl:24-132, quirks included): one thread per ray
+// ------------------------------------------------------------------------------------------------
+struct LaunchArgs {
+    int n_launchers, n_rings, n_per;   // rays per launcher (identical for all: N_theta depends on the rings only)
+    const double* x0;                  // [3][nl]
+    const double* N0;                  // [3][nl]
+    const double* w;                   // [nl] beam width
+    const double* inv_Rc;              // [nl] inverse curvature radius (inf = paraxial)
+    const double* f;                   // [nl]
+    const int* mode;                   // [nl]
+    const double* r_unit;              // [n_rings] Gauss-Hermite radii / (w/sqrt2)
+    const double* rw_unit;             // [n_rings] Gauss-Hermite weights / (w/sqrt2)
+    const int* ring_start;             // [n_rings+1] prefix sum of N_theta
+    double wsum_unit;                  // sum_i r_i rw_i 2 pi in unit widths (weights of one launcher sum to wsum_unit w^2/2)
+    int normalize;
+    // outputs: bundle arrays over n = nl * n_per rays
+    double *pos, *dir, *weight, *freq;
+    int *mode_out, *beam;
+};
+
+__global__ void k_launch_rays(LaunchArgs A) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)A.n_launchers * A.n_per;
+    if (g >= n) return;
+    const int L = (int)(g / A.n_per), k = (int)(g % A.n_per);
+    int ring = 0;
+    while (ring + 1 < A.n_rings && k >= A.ring_start[ring + 1]) ++ring;
+    const int j = k - A.ring_start[ring], nth = A.ring_start[ring + 1] - A.ring_start[ring];
+    const int nl = A.n_launchers;
+    const double x0[3] = {A.x0[L], A.x0[nl + L], A.x0[2 * nl + L]};
+    double n0[3] = {A.N0[L], A.N0[nl + L], A.N0[2 * nl + L]};
+    const double nn = sqrt(n0[0] * n0[0] + n0[1] * n0[1] + n0[2] * n0[2]);
+    for (int c = 0; c < 3; ++c) n0[c] /= nn;
+    const double w = A.w[L], irc = A.inv_Rc[L], f = A.f[L];
+    const bool curved = isfinite(irc);
+    double w0 = w, xw[3] = {0, 0, 0};
+    if (curved) {  // src/launch.jl:34-47
+        const double Rc = 1.0 / irc, lam = TORJ_C / f;
+        const double den = lam * lam * Rc * Rc + M_PI * M_PI * w * w * w * w;
+        w0 = (lam * fabs(Rc) * w) / sqrt(den);
+        const double zw = M_PI * M_PI * Rc * w * w * w * w / den;
+        for (int c = 0; c < 3; ++c) xw[c] = x0[c] - n0[c] * zw;
+    }
+    double ec[3] = {1.0, 0.0, -n0[0] / n0[2]};                       // src/launch.jl:54-57
+    double eu[3] = {-n0[0] * n0[1] / n0[2], n0[2] - n0[0], -n0[1]};  // src/launch.jl:61-64
+    const double nc = sqrt(ec[0] * ec[0] + ec[1] * ec[1] + ec[2] * ec[2]), nu = sqrt(eu[0] * eu[0] + eu[1] * eu[1] + eu[2] * eu[2]);
+    for (int c = 0; c < 3; ++c) { ec[c] /= nc; eu[c] /= nu; }
+    const double sc = w / sqrt(2.0);
+    const double r = A.r_unit[ring] * sc, rw = A.rw_unit[ring] * sc;
+    const double th = 2.0 * M_PI * (double)j / (double)nth;
+    const double chi = r * cos(th), ups = r * sin(th);
+    double p[3], d[3];
+    for (int c = 0; c < 3; ++c) p[c] = chi * ec[c] + ups * eu[c] + x0[c];
+    if (curved) {  // src/launch.jl:102-113
+        const double sg = irc > 0.0 ? 1.0 : (irc < 0.0 ? -1.0 : 0.0);
+        for (int c = 0; c < 3; ++c) d[c] = w0 / w * (chi * ec[c] + ups * eu[c]) * sg + xw[c];
+        if (irc < 0.0) { for (int c = 0; c < 3; ++c) d[c] -= p[c]; }
+        else { for (int c = 0; c < 3; ++c) d[c] = -d[c] + p[c]; }
+        const double dn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int c = 0; c < 3; ++c) d[c] /= dn;
+    } else {
+        for (int c = 0; c < 3; ++c) d[c] = n0[c];
+    }
+    double wt = r * rw * (2.0 * M_PI / (double)nth);                 // src/launch.jl:120
+    if (A.normalize) wt /= (A.wsum_unit * sc * sc);                  // src/launch.jl:125-126
+    else wt *= 2.0 / (w * w * M_PI);
+    for (int c = 0; c < 3; ++c) { A.pos[c * n + g] = p[c]; A.dir[c * n + g] = d[c]; }
+    A.weight[g] = wt;
+    A.freq[g] = f;
+    A.mode_out[g] = A.mode[L];
+    A.beam[g] = L;
+}
+
 // dependent-issue latency of DFMA: one warp, one chain, cycles from clock64()
 __global__ void k_dfma_latency(int iters, double seed, double* out, long long* cycles) {
     double a = seed;

@@ -97,11 +97,54 @@ def make_beam(plasma: Plasma, r, phi, z, steering_angle_tor, steering_angle_pol,
     return arc, traj, powers, res["dP_dV"], res["deposited_power"], wts
 
 
-def make_beams(plasma: Plasma, launchers, s_max, psi_dP_dV, *, options=None, ctx=None, **kwargs):
+def _make_beams_device(plasma, launchers, s_max, psi_dP_dV, options, ctx, N_rings=3, min_azimuthal_points=5,
+                       normalize_weight_sum=True):
+    """Rays generated on the GPU (torj_bundle_create_from_launchers), traced and reduced there; only launcher
+    parameters go in and profiles / per-ray scalars come out."""
+    ctx = ctx or _lib.context()
+    L = _lib.lib()
+    if N_rings < 2:
+        raise ValueError(f"N_rings = {N_rings} < 2 which is the minimum")
+    nl = len(launchers)
+    x0 = np.array([[q["r"] * np.cos(q["phi"]), q["r"] * np.sin(q["phi"]), q["z"]] for q in launchers]).T.copy()
+    N0 = np.array([pol_tor_angles_2_vector(q["steering_angle_pol"], q["steering_angle_tor"]) for q in launchers]).T.copy()
+    w = np.array([q["spot_size"] for q in launchers], dtype=np.float64)
+    irc = np.array([q["inverse_curvature_radius"] for q in launchers], dtype=np.float64)
+    f = np.array([q["f"] for q in launchers], dtype=np.float64)
+    md = np.array([q["mode"] for q in launchers], dtype=np.int32)
+    gx, gw = np.polynomial.hermite.hermgauss(2 * N_rings + 2)
+    bh = _lib.c_vp(); n = C.c_int64()
+    _lib.check(L.torj_bundle_create_from_launchers(ctx, nl, _p(x0), _p(N0), _p(w), _p(irc), _p(f), md.ctypes.data_as(c_ip),
+                                                   int(N_rings), int(min_azimuthal_points), int(bool(normalize_weight_sum)),
+                                                   _p(np.ascontiguousarray(gx)), _p(np.ascontiguousarray(gw)), C.byref(bh),
+                                                   C.byref(n)))
+    try:
+        n = int(n.value)
+        psi = np.ascontiguousarray(psi_dP_dV, dtype=np.float64)
+        opt = options or _lib.default_options()
+        _lib.check(L.torj_bundle_trace(bh, plasma.handle(ctx), C.byref(opt), float(s_max), len(psi), _p(psi)))
+        prof = np.zeros((nl, len(psi))); dep = np.zeros(nl)
+        Pf = np.zeros(n); Pd = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
+        cnt = _lib.TorjCounters()
+        _lib.check(L.torj_bundle_results(bh, _p(prof), _p(dep), _p(Pf), _p(Pd), npts.ctypes.data_as(c_ip),
+                                         st.ctypes.data_as(c_ip), C.byref(cnt)))
+        wt = np.zeros(n)
+        _lib.check(L.torj_bundle_rays(bh, None, None, _p(wt)))
+    finally:
+        L.torj_bundle_destroy(bh)
+    per = n // nl
+    res = dict(dP_dV=prof, deposited_power=dep, P_final=Pf, P_deposited_ray=Pd, n_points=npts, status=st,
+               counters=cnt.as_dict())
+    return prof, dep, [wt[i * per:(i + 1) * per] for i in range(nl)], [Pf[i * per:(i + 1) * per] for i in range(nl)], res
+
+
+def make_beams(plasma: Plasma, launchers, s_max, psi_dP_dV, *, options=None, ctx=None, device_launch=False, **kwargs):
     """Batched make_beam for scans: `launchers` is a sequence of dicts with the positional arguments of make_beam
     (r, phi, z, steering_angle_tor, steering_angle_pol, spot_size, inverse_curvature_radius, f, mode). All beams are
     traced in ONE device call; returns (dP_dV[n_beams, n_psi], deposited_power[n_beams], ray_weights per beam,
     P_final per beam). Equivalent to a host loop over make_beam (reference src/solve.jl:209-242) without trajectories."""
+    if device_launch:
+        return _make_beams_device(plasma, launchers, s_max, psi_dP_dV, options, ctx, **kwargs)
     P, D, W, F, M, B = [], [], [], [], [], []
     for b, L in enumerate(launchers):
         N0 = pol_tor_angles_2_vector(L["steering_angle_pol"], L["steering_angle_tor"])
