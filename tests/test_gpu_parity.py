@@ -30,6 +30,11 @@ def l2rel(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _abs_al_init():
+    tj.abs_Al_init(24)  # reference test/tests/setup.jl:80
+
+
 @pytest.fixture(scope="module")
 def gpu_full(arrays_full):
     tj.abs_Al_init(24)  # reference test/tests/setup.jl:80
@@ -346,6 +351,48 @@ def test_config5_high_te_third_harmonic_scan(gl24):
         assert abs(dep[b] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
         assert l2rel(dP[b], ref["dP_dV"]) < L2_FAITHFUL
     assert dep[2] > 0.99 and Pf[2].max() > 1e-5           # 170 GHz: strong but incomplete third-harmonic absorption
+
+
+def test_randomised_rays_against_oracle(arrays_small, gl24):
+    """Seeded random launchers (position, angles, frequency 60-180 GHz, X/O mode) on equilibria with scaled density and
+    temperature: statuses, step counts, final power and end points must agree ray by ray, including the rays that fail
+    to initialise (no bracket, cut-off)."""
+    rng = np.random.default_rng(20261018)
+    psi = np.linspace(0, 1, 60)
+    n_checked = n_bad = 0
+    for trial in range(3):
+        arr = dict(arrays_small)
+        arr["ne_prof"] = arr["ne_prof"] * rng.uniform(0.3, 2.5)
+        arr["Te_prof"] = arr["Te_prof"] * rng.uniform(0.2, 4.0)
+        pl = tj.Plasma(*arr.values()); opl = O.OraclePlasma(*arr.values())
+        n = 48
+        z0 = rng.uniform(-0.6, 0.6, n); R0 = rng.uniform(2.35, 2.9, n); ph = rng.uniform(-0.3, 0.3, n)
+        pol = np.deg2rad(rng.uniform(-40, 40, n)) + np.arctan2(z0, R0 - 1.7) * 0.8
+        tor = np.deg2rad(rng.uniform(-25, 25, n))
+        pos = np.stack([R0 * np.cos(ph), R0 * np.sin(ph), z0], 1)
+        dirs = np.stack([tj.pol_tor_angles_2_vector(p, t) for p, t in zip(pol, tor)])
+        f = rng.choice([60e9, 82.7e9, 95e9, 110e9, 140e9, 170e9], n)
+        mode = rng.choice([1, -1], n)
+        w = np.full(n, 1.0 / n)
+        res = tj.trace_bundle(pl, pos, dirs, w, f, mode, 0.8, psi, options=tj.default_options(n_segments=40),
+                              trajectories=(0, n), traj_max_pts=2 + 40 * 210)
+        ref = opl.trace_bundle(pos, dirs, w, f, mode, 0.8, psi, gl24, opts=O.OracleOptions.default(n_segments=40),
+                               deposition="streaming")
+        assert np.array_equal(res["status"], ref["status"]), (res["status"], ref["status"])
+        ok = ref["status"] == 0
+        n_checked += int(ok.sum()); n_bad += int((~ok).sum())
+        assert np.array_equal(res["n_points"][ok], ref["n_points"][ok])
+        assert np.abs(res["P_final"][ok] - ref["P_final"][ok]).max() < 1e-9
+        if ref["deposited_power"] > 1e-9:
+            assert abs(res["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"] + 1e-12
+            assert l2rel(res["dP_dV"], ref["dP_dV"]) < 1e-6
+        for i in np.nonzero(ok)[0][:6]:
+            ro = opl.make_ray(pos[i], dirs[i], f[i], int(mode[i]), 0.8, psi, gl24, opts=O.OracleOptions.default(n_segments=40))
+            m = int(res["n_points"][i])
+            assert m == len(ro["s"])
+            end = res["traj_xyz"][i, :, m - 1]
+            assert max(abs(end[0] - ro["x"][-1]), abs(end[1] - ro["y"][-1]), abs(end[2] - ro["z"][-1])) < TRAJ_TOL
+    assert n_checked > 60 and n_bad > 0      # the sample must contain both traced and rejected rays
 
 
 def test_smallest_inputs(gpu_small, launcher):
