@@ -53,7 +53,9 @@ typedef struct torj_options {
     double psi_stop;               /* 1.0   src/solve.jl:174 */
     double p_stop;                 /* 1e-6  src/solve.jl:176 */
     double te_min;                 /* 20 eV src/absorption.jl:194 */
-    int32_t max_harmonic;          /* 3     src/absorption.jl:199 */
+    int32_t max_harmonic;          /* 3     src/absorption.jl:199; 1 = no absorption, 4..16 add the harmonics the reference
+                                      leaves out with the same integral (src/absorption.jl:170-189), Bessel functions
+                                      from libm jn() */
     int32_t max_steps_per_segment; /* safety cap, 100000 */
     double alpha_floor;            /* 1e-14 m^-1: a harmonic integral (src/absorption.jl:170-189) is skipped when a rigorous
                                       upper bound of its contribution to alpha is below this (|J_n|<=1, sum of weights 2,

@@ -395,6 +395,44 @@ def test_randomised_rays_against_oracle(arrays_small, gl24):
     assert n_checked > 60 and n_bad > 0      # the sample must contain both traced and rejected rays
 
 
+def test_harmonics_above_the_third(gl24):
+    """torj_options.max_harmonic > 3: the harmonics the reference leaves out
+    (src/absorption.jl:199,213), same integral, against the oracle's loop over m = 2..max_harmonic. 225 GHz in the
+    25 keV Solov'ev plasma is absorbed at the fourth and fifth harmonic only."""
+    arr = tj.solovev_arrays(65, 65, Te0=25e3, ne0=6e19)
+    pl = tj.Plasma(*arr.values()); opl = O.OraclePlasma(*arr.values())
+    psi = np.linspace(0, 1, 100)
+    x0 = np.array([2.5, 0.0, 0.4]); N0 = tj.pol_tor_angles_2_vector(np.deg2rad(30.0), 0.1)
+    pos, dirs, w = tj.launch_peripheral_rays(x0, N0, 0.0174, 1 / 3.99, 225e9, N_rings=2, min_azimuthal_points=3)
+    absorbed = {}
+    for mh in (1, 3, 4, 5):
+        res = tj.trace_bundle(pl, pos, dirs, w, 225e9, 1, 1.0, psi, options=tj.default_options(max_harmonic=mh, n_segments=50))
+        ref = opl.trace_bundle(pos, dirs, w, 225e9, 1, 1.0, psi, gl24, opts=O.OracleOptions.default(max_harmonic=mh, n_segments=50),
+                               deposition="streaming")
+        assert (res["status"] == 0).all() and np.array_equal(res["n_points"], ref["n_points"])
+        assert np.abs(res["P_final"] - ref["P_final"]).max() < 1e-9
+        absorbed[mh] = res["deposited_power"]
+        if mh <= 3:
+            assert res["deposited_power"] == 0.0 and res["counters"]["n_harm"] == 0
+        else:
+            assert abs(res["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+            assert l2rel(res["dP_dV"], ref["dP_dV"]) < 1e-6
+    assert 0.5 < absorbed[4] < absorbed[5] < 1.0 + 1e-12
+
+
+def test_option_validation(gpu_small, launcher):
+    psi = np.linspace(0, 1, 10)
+    for bad in (dict(max_harmonic=0), dict(max_harmonic=17), dict(scheme=2), dict(n_segments=0), dict(dtmax=0.0),
+                dict(abstol=-1.0), dict(alpha_floor=-1.0), dict(max_steps_per_segment=0)):
+        with pytest.raises(tj.TorjError):
+            tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, psi,
+                            options=tj.default_options(**bad))
+    with pytest.raises(tj.TorjError):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.0, psi)
+    with pytest.raises(tj.TorjError):
+        tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, psi[::-1].copy())
+
+
 def test_smallest_inputs(gpu_small, launcher):
     r = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, np.array([0.0, 1.0]))
     assert r["status"][0] == 0 and r["dP_dV"].shape == (2,) and r["dP_dV"][1] == 0.0

@@ -693,6 +693,10 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (od.scheme != 0 && od.scheme != 1) FAIL("torj_bundle_trace: scheme must be 0 (Tsit5) or 1 (OwrenZen3)");
     if (od.n_segments < 1) FAIL("torj_bundle_trace: n_segments < 1");
     if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
+    if (od.max_harmonic < 1 || od.max_harmonic > 16) FAIL("torj_bundle_trace: max_harmonic must be in 1..16 (1 = no absorption)");
+    if (!(od.dtmax > 0.0) || !(od.abstol > 0.0) || !(od.reltol > 0.0)) FAIL("torj_bundle_trace: dtmax, abstol and reltol must be > 0");
+    if (od.max_steps_per_segment < 1) FAIL("torj_bundle_trace: max_steps_per_segment < 1");
+    if (!(s_max > 0.0)) FAIL("torj_bundle_trace: s_max must be > 0");
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
     if (b->n_psi != n_psi || b->prof_rows != b->n_beams) {
@@ -744,18 +748,15 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     int bps = 0;
     int64_t warps = (b->n + 31) / 32;
     int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);
-    if (od.scheme == 0) {
-        CK(cudaFuncSetAttribute(k_trace<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<0>, TORJ_TPB, smem));
-    } else {
-        CK(cudaFuncSetAttribute(k_trace<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<1>, TORJ_TPB, smem));
-    }
+    // harmonics above the third run in their own instantiations, so the default kernels do not carry the code
+    void (*kern)(TraceArgs) = od.max_harmonic > 3 ? (od.scheme == 0 ? k_trace<0, true> : k_trace<1, true>)
+                                                  : (od.scheme == 0 ? k_trace<0, false> : k_trace<1, false>);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TORJ_TPB, smem));
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
     int64_t grid = std::min<int64_t>((int64_t)c->num_sms * bps, blocks_needed);  // persistent: resident CTAs only
     CK(cudaEventRecord(c->ev0, st));
-    if (od.scheme == 0) k_trace<0><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
-    else k_trace<1><<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+    kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, st));

@@ -464,7 +464,7 @@ struct HarmCoef {  // per-harmonic invariants
 
 // reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M
 template <int M, int K, bool GENERIC>
-__device__ __forceinline__ double harmonic_sum(const HarmCoef& c) {
+__device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) {
     double sum = 0.0;
     const int n = c_gl.n;
     TORJ_PRAGMA_NODE_UNROLL
@@ -474,8 +474,8 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c) {
         const double z = c.x_m * sq;
         double J, D;
         if (GENERIC) {
-            J = jn(M, z);
-            D = 0.5 * z * (jn(M - 1, z) - jn(M + 1, z));
+            J = jn(m_rt, z);
+            D = 0.5 * z * (jn(m_rt - 1, z) - jn(m_rt + 1, z));
         } else {
             const double hz = 0.5 * z;
             bessel_JD<M, K>(hz, hz * hz, J, D);
@@ -507,9 +507,11 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef& c) {
 // One sqrt per harmonic; everything else is products of the reciprocals prepared in abs_albajar.
 // `safe` is cleared unless the bound is below floor * TORJ_SKIP_MARGIN (see abs_albajar).
 #define TORJ_SKIP_MARGIN 1e-10
+// M = 0: order given at run time (harmonics above the reference's third; libm jn() throughout).
 template <int M>
-__device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe) {
-    const double fm = (double)M, ifm = 1.0 / (double)M;
+__device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe, int m_rt = M) {
+    const int m = M ? M : m_rt;
+    const double fm = (double)m, ifm = 1.0 / (double)m;
     const double A = fm * h.Y * h.ispar;  // m / m_0, m_0 = spar / Y
     double q2 = A * A - 1.0;
     q2 = q2 > 0.0 ? q2 : 0.0;
@@ -546,8 +548,28 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     }
     safe = false;
     cnt.n_harm++;
-    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false>(c);
-    return harmonic_sum_large<M>(c);
+    if (M == 0) return harmonic_sum<2, 1, true>(c, m);
+    if (c.x_m <= 3.2) return harmonic_sum<(M ? M : 2), 12, false>(c);
+    return harmonic_sum_large<(M ? M : 2)>(c);
+}
+
+// Harmonics 4..max_harmonic (torj_options.max_harmonic > 3; the reference stops at 3, src/absorption.jl:199). Cold and
+// out of line: the hot loop pays one uniform compare for it.
+struct HighHarm {
+    double alpha;
+    int n_harm, n_prune;
+    bool safe;
+};
+__device__ __noinline__ HighHarm harmonics_above_3(const HarmPre& h, int max_harmonic, double m_0, bool safe) {
+    HighHarm r;
+    Counters cnt = {};
+    r.alpha = 0.0;
+    for (int m = 4; m <= max_harmonic; ++m) {
+        if ((double)m >= m_0) r.alpha += harmonic_alpha<0>(h, cnt, safe, m);
+        else if (!(m_0 - (double)m > 0.02 * m_0)) safe = false;
+    }
+    r.n_harm = (int)cnt.n_harm; r.n_prune = (int)cnt.n_prune; r.safe = safe;
+    return r;
 }
 
 // reference src/absorption.jl:191-226 (+ the T_e evaluation of :233). omega enters only through omega/c.
@@ -556,6 +578,9 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
 // (in m_0) from becoming eligible. The integrator then takes alpha = 0 at the inner Runge-Kutta stages of the NEXT
 // step, which lie within dtmax (0.1 mm) of this point: the bound would have to grow by 1e10 (its exponent by 23)
 // and m_0 = sqrt(1-N_par^2)/Y to move by 2 % over a distance far below the cell size of the spline tables.
+// HIGH: the instantiation that also sums harmonics 4..max_harmonic (kept out of the default kernels: even an
+// out-of-line call on a never-taken branch cost 6 % there, through the stack copy of HarmPre and its spills).
+template <bool HIGH>
 __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double iY, double N2, double N_par,
                                               double lnTe, Counters& cnt, bool& skip_ok) {
     skip_ok = false;
@@ -605,6 +630,10 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
         if (3.0 >= m_0) alpha += harmonic_alpha<3>(h, cnt, safe);
         else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
     }
+    if (HIGH && rc.max_harmonic >= 4) {
+        const HighHarm r = harmonics_above_3(h, rc.max_harmonic, m_0, safe);
+        alpha += r.alpha; cnt.n_harm += r.n_harm; cnt.n_prune += r.n_prune; safe = r.safe;
+    }
     skip_ok = safe;
     return alpha;
 }
@@ -620,7 +649,7 @@ struct PointVals {
 // WITH_PSI: du[7] = psi_N at the point and du[8] = grad(psi_N) . dx/ds (inputs of the streaming deposition)
 // alpha_skip (in/out, optional): on entry true = take alpha = 0 without evaluating it (see abs_albajar); on exit, when
 // alpha was evaluated, whether the next step's inner stages may skip it.
-template <bool WITH_ALPHA, bool WITH_PSI = false>
+template <bool WITH_ALPHA, bool WITH_PSI = false, bool HIGH = false>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
                                     PointVals* pv = nullptr, bool skip_alpha = false, bool* skip_ok = nullptr) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
@@ -670,7 +699,7 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
             cnt.n_askip++;
         } else {
             bool ok;
-            const double alpha = abs_albajar(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
+            const double alpha = abs_albajar<HIGH>(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
             du[6] = -u[6] * alpha;
             if (skip_ok) *skip_ok = ok;
         }

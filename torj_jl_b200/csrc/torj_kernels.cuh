@@ -318,7 +318,8 @@ enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT 
 #define TORJ_TRACE_BOUNDS __launch_bounds__(TORJ_TPB, TORJ_MINB)
 #endif
 
-template <int SCH>
+// HIGH = true: harmonics above the third enabled (torj_options.max_harmonic > 3); see abs_albajar
+template <int SCH, bool HIGH = false>
 __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
@@ -451,7 +452,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // with a 1e10 margin (abs_albajar)
         if (phase != PH_IDLE) {
             const bool inner = (phase == PH_STAGE && st < S - 1);
-            rhs<true, TORJ_PSI_IN_RHS != 0>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
+            rhs<true, TORJ_PSI_IN_RHS != 0, HIGH>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
             if (!inner) a_skip = a_skip_next;
         }
 #if !TORJ_PSI_IN_RHS
@@ -718,7 +719,7 @@ __global__ void k_probe(DevTables T, long long n, const double* x, const double*
     double u[7] = {x[i], x[n + i], x[2 * n + i], N[i], N[n + i], N[2 * n + i], 1.0}, du[7];
     Counters c = {0, 0, 0, 0, 0, 0, 0};
     PointVals pv;
-    rhs<true>(T, rc, u, du, c, &pv);
+    rhs<true, false, true>(T, rc, u, du, c, &pv);
     double Babs = pv.Y / rc.cY;
     out[i] = psi_at(T, u);
     out[n + i] = pv.X / rc.cX;
@@ -736,7 +737,7 @@ __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int m
     double uu[7], dd[7];
     for (int q = 0; q < 7; ++q) uu[q] = u[(size_t)q * n + i];
     Counters c = {0, 0, 0, 0, 0, 0, 0};
-    rhs<true>(T, rc, uu, dd, c);
+    rhs<true, false, true>(T, rc, uu, dd, c);
     for (int q = 0; q < 7; ++q) du[(size_t)q * n + i] = dd[q];
 }
 
