@@ -226,8 +226,13 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
 
 // one field (0..3 from tabA, 4 = lnTe, 5 = psi) with value, gradient and mixed derivative, any position:
 // "Line" extrapolation  v = itp(xc) + sum_d (x_d - xc_d) g_d(xc)  and the gradient of that expression
-__device__ __noinline__ void eval_field_ext(const DevTables& T, int field, double R, double Z, double* val, double* dR,
-                                            double* dZ) {
+// Out of line and cold (rays are inside the grid except for a few steps at the edge). Table descriptor BY VALUE and
+// results BY VALUE: a reference or pointer parameter here forces the caller's copy of the descriptor and its result
+// registers into local memory on the HOT path as well (measured: 35 local loads/stores per RHS).
+struct Ext3 {
+    double v, dR, dZ;
+};
+__device__ __noinline__ Ext3 eval_field_ext(const DevTables T, int field, double R, double Z) {
     double Rc = fmin(fmax(R, T.r0), T.rlast), Zc = fmin(fmax(Z, T.z0), T.zlast);
     double wr[4], dwr[4], wz[4], dwz[4];
     int br = bs_locate(Rc, T.r0, T.inv_hr, T.nR, wr, dwr);
@@ -254,7 +259,9 @@ __device__ __noinline__ void eval_field_ext(const DevTables& T, int field, doubl
     double v = s, vR = sR, vZ = sZ;
     if (outR) { v += (R - Rc) * sR; if (!outZ) vZ += (R - Rc) * sRZ; }
     if (outZ) { v += (Z - Zc) * sZ; if (!outR) vR += (Z - Zc) * sRZ; }
-    *val = v; *dR = vR; *dZ = vZ;
+    Ext3 r;
+    r.v = v; r.dR = vR; r.dZ = vZ;
+    return r;
 }
 
 __device__ __forceinline__ bool inside_grid(const DevTables& T, double R, double Z) {
@@ -266,21 +273,22 @@ __device__ __forceinline__ void eval_fields(const DevTables& T, double R, double
     if (inside_grid(T, R, Z)) {
         eval_fields_in<WITH_PSI>(T, R, Z, f);
     } else {
-        double d0, d1;
-        eval_field_ext(T, 0, R, Z, &f.BR, &f.BR_R, &f.BR_Z);
-        eval_field_ext(T, 1, R, Z, &f.BZ, &f.BZ_R, &f.BZ_Z);
-        eval_field_ext(T, 2, R, Z, &f.Bp, &f.Bp_R, &f.Bp_Z);
-        eval_field_ext(T, 3, R, Z, &f.L, &f.L_R, &f.L_Z);
-        eval_field_ext(T, 4, R, Z, &f.lnTe, &d0, &d1);
+        Ext3 e;
+        e = eval_field_ext(T, 0, R, Z); f.BR = e.v; f.BR_R = e.dR; f.BR_Z = e.dZ;
+        e = eval_field_ext(T, 1, R, Z); f.BZ = e.v; f.BZ_R = e.dR; f.BZ_Z = e.dZ;
+        e = eval_field_ext(T, 2, R, Z); f.Bp = e.v; f.Bp_R = e.dR; f.Bp_Z = e.dZ;
+        e = eval_field_ext(T, 3, R, Z); f.L = e.v; f.L_R = e.dR; f.L_Z = e.dZ;
+        e = eval_field_ext(T, 4, R, Z); f.lnTe = e.v;
         f.psi = f.psi_R = f.psi_Z = 0.0;
-        if (WITH_PSI) eval_field_ext(T, 5, R, Z, &f.psi, &f.psi_R, &f.psi_Z);
+        if (WITH_PSI) { e = eval_field_ext(T, 5, R, Z); f.psi = e.v; f.psi_R = e.dR; f.psi_Z = e.dZ; }
     }
 }
 
 // psi_N with gradient (reference src/plasma.jl:61-65 on psi_norm_spline; src/solve.jl:63)
 __device__ __forceinline__ void eval_psi(const DevTables& T, double R, double Z, double* psi, double* pR, double* pZ) {
     if (!inside_grid(T, R, Z)) {
-        eval_field_ext(T, 5, R, Z, psi, pR, pZ);
+        const Ext3 e = eval_field_ext(T, 5, R, Z);
+        *psi = e.v; *pR = e.dR; *pZ = e.dZ;
         return;
     }
     double wr[4], dwr[4], wz[4], dwz[4];
@@ -496,7 +504,7 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
 
 // rarely taken variants kept out of line so the hot code stays small (instruction cache)
 template <int M>
-__device__ __noinline__ double harmonic_sum_large(const HarmCoef& c) {
+__device__ __noinline__ double harmonic_sum_large(const HarmCoef c) {  // by value: see eval_field_ext
     if (c.x_m <= 6.5) return harmonic_sum<M, 24, false>(c);
     return harmonic_sum<M, 1, true>(c);
 }
