@@ -202,6 +202,9 @@ int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* 
 int torj_fp64_peak(torj_ctx* ctx, int32_t iters, double* tflops, double* ms);
 /* Dependent-issue latency of DFMA in cycles (one warp, one chain): how much ILP x TLP the FP64 pipe needs. */
 int torj_fp64_latency(torj_ctx* ctx, int32_t iters, double* cycles_per_dfma);
+/* The kernels' own reciprocal, reciprocal square root, square root and exp (MUFU seed + FMA correction; branch-free
+   exp) on n host values x > 0 (exp: any |x| <= 708): out[4][n] in that order. For accuracy tests against libm. */
+int torj_math_probe(torj_ctx* ctx, int64_t n, const double* x, double* out);
 
 #ifdef __cplusplus
 }

@@ -594,3 +594,26 @@ def test_fp64_peak_probe_and_launch_counter():
     _lib.check(tj.lib().torj_fp64_peak(ctx, 4000, C.byref(tf), C.byref(ms)))
     assert 20.0 < tf.value < 45.0                                  # nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2
     assert tj.lib().torj_ctx_launch_count(ctx) == n0 + 2
+
+
+def test_device_elementary_functions_against_libm():
+    """rcp_fast / rsqrt_fast / sqrt_fast / exp_fast (MUFU seed + one third-order FMA correction; branch-free exp) against
+    numpy in units of the last place, over the magnitudes the path produces (1e-30 .. 1e30; exponents in +-700)."""
+    import ctypes as C
+    from torj_jl_b200 import _lib
+    rng = np.random.default_rng(7)
+    x = np.concatenate([10.0 ** rng.uniform(-30, 30, 200000), rng.uniform(0.5, 2.0, 100000),
+                        np.nextafter(2.0 ** np.arange(-40, 40), np.inf), 2.0 ** np.arange(-40, 40)])
+    out = np.empty((4, x.size))
+    _lib.check(tj.lib().torj_math_probe(_lib.context(), x.size, x.ctypes.data_as(_lib.c_dp), out.ctypes.data_as(_lib.c_dp)))
+    ld = np.longdouble   # x87 extended precision: 11 more bits than double
+    assert np.finfo(ld).nmant >= 63
+    ulp = lambda got, ref: float(np.max(np.abs(got.astype(ld) - ref) / np.spacing(np.abs(ref.astype(np.float64))).astype(ld)))
+    xl = x.astype(ld)
+    assert ulp(out[0], 1 / xl) <= 1.0
+    assert ulp(out[1], 1 / np.sqrt(xl)) <= 1.5
+    assert ulp(out[2], np.sqrt(xl)) <= 1.0
+    e = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-1, 1, 100000), [0.0, -708.0, 708.0, -800.0]])
+    out = np.empty((4, e.size))
+    _lib.check(tj.lib().torj_math_probe(_lib.context(), e.size, e.ctypes.data_as(_lib.c_dp), out.ctypes.data_as(_lib.c_dp)))
+    assert ulp(out[3], np.exp(np.clip(e, -708.0, 708.0).astype(ld))) <= 1.5

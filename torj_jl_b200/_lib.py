@@ -84,6 +84,7 @@ SIGNATURES = {
                                    C.c_int64, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TorjCounters)]),
     "torj_fp64_peak": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
     "torj_fp64_latency": (C.c_int, [c_vp, C.c_int32, c_dp]),
+    "torj_math_probe": (C.c_int, [c_vp, C.c_int64, c_dp, c_dp]),
 }
 
 

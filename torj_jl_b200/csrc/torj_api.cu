@@ -1025,4 +1025,21 @@ int torj_fp64_latency(torj_ctx* c, int32_t iters, double* cycles_per_dfma) {
     return 0;
 }
 
+// rcp_fast / rsqrt_fast / sqrt_fast / exp_fast of the device code on host arrays: out[4][n]
+int torj_math_probe(torj_ctx* c, int64_t n, const double* x, double* out) {
+    if (!c || n < 1 || !x || !out) FAIL("torj_math_probe: bad argument");
+    if (set_device(c)) return 1;
+    double *dx, *dout;
+    CK(cudaMalloc(&dx, n * sizeof(double)));
+    CK(cudaMalloc(&dout, 4 * n * sizeof(double)));
+    CK(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_math_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dx, dout);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dx); cudaFree(dout);
+    return 0;
+}
+
 }  // extern "C"

@@ -104,32 +104,34 @@ struct Counters {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Branch-free FP64 reciprocal / reciprocal square root / square root: MUFU seed (rcp/rsqrt.approx.ftz.f64, ~2^-22)
-// + two Newton steps in FMA arithmetic (error ~1 ulp).  The library's IEEE division and sqrt cost 3-4x the
-// instructions and carry a slow-path branch each; the hot path has ~25 of them per RHS.  Arguments here are
-// normal, positive (or non-zero for rcp) numbers; zero is handled where it can occur (sqrt_fast).
+// Branch-free FP64 reciprocal / reciprocal square root / square root: MUFU seed (rcp/rsqrt.approx.ftz.f64 work on
+// the upper 32 bits of the operand: relative error e0 ~ 2^-20) + ONE third-order correction in FMA arithmetic
+// (residual ~e0^3 = 2^-60, i.e. the result is good to the rounding of the last FMA, ~1 ulp). Two Newton steps reach
+// the same accuracy with 1 (rcp) / 3 (rsqrt) more instructions and a dependency chain one longer. The library's IEEE
+// division and sqrt cost 3-4x the instructions and carry a slow-path branch each; the hot path has ~25 of them per
+// RHS. Arguments here are normal, positive (or non-zero for rcp) numbers; zero is handled where it can occur
+// (sqrt_fast).
 // ------------------------------------------------------------------------------------------------
 __device__ TORJ_MATH_INLINE double rcp_fast(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    const double e = fma(-x, r, 1.0);        // 1/x = r / (1 - e) = r (1 + e + e^2 + ...)
+    return fma(r, fma(e, e, e), r);
 }
 __device__ TORJ_MATH_INLINE double rsqrt_fast(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x * y, 0.5 * y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-x * y, 0.5 * y, 0.5);
-    return fma(y, e, y);
+    const double e = fma(-x * y, y, 1.0);    // x^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3 e^2/8 + ...)
+    return fma(y, fma(0.375, e, 0.5) * e, y);
 }
 __device__ TORJ_MATH_INLINE double sqrt_fast(double x) {  // x >= 0
-    double y = rsqrt_fast(x);
-    double s = x * y;
-    s = fma(fma(-s, s, x), 0.5 * y, s);
-    return x > 0.0 ? s : 0.0;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, 0.5 * y, 0.5);
+    y = fma(y, e, y);                        // one Newton step: relative error ~2^-40
+    const double s = x * y;
+    const double r = fma(fma(-s, s, x), 0.5 * y, s);   // s (1 + d) -> s (1 - d^2)
+    return x > 0.0 ? r : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -915,4 +915,15 @@ __global__ void k_dfma_latency(int iters, double seed, double* out, long long* c
     if (threadIdx.x == 0) { cycles[0] = t1 - t0; out[0] = a; }
 }
 
+// the kernel's own elementary functions on n arguments (accuracy tests): out[0..3][n] = rcp, rsqrt, sqrt, exp
+__global__ void k_math_probe(long long n, const double* x, double* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[i] = rcp_fast(v);
+    out[n + i] = rsqrt_fast(v);
+    out[2 * n + i] = sqrt_fast(v);
+    out[3 * n + i] = exp_fast(v);
+}
+
 }  // namespace torj
