@@ -745,6 +745,9 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
 #if TORJ_K_SMEM
     smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
 #endif
+#if TORJ_PARK
+    smem += (size_t)TORJ_PARK_SLOTS * TORJ_TPB * sizeof(double);
+#endif
     int bps = 0;
     int64_t warps = (b->n + 31) / 32;
     int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);

@@ -30,6 +30,9 @@ namespace torj {
 #ifndef TORJ_EXP_ESTRIN
 #define TORJ_EXP_ESTRIN 0
 #endif
+#ifndef TORJ_HARM_RT
+#define TORJ_HARM_RT 0  // 1: harmonics 2 and 3 share one run-time-order copy of the quadrature code
+#endif
 #ifndef TORJ_NODE_UNROLL
 #define TORJ_NODE_UNROLL 1
 #endif
@@ -446,15 +449,17 @@ __device__ TORJ_MATH_INLINE double exp_fast(double x) {
 // The reference's three Bessel functions enter abs_Al_pol_fact (src/absorption.jl:152-165) only through
 //   J_M^2,  J_M (J_{M-1} - J_{M+1}) = 2 J_M J_M',  J_{M-1} J_{M+1} = (M J_M / z)^2 - J_M'^2
 // so two series suffice and nothing is divided by z.
+// M = 0: order m_rt (2 or 3) chosen at run time — one copy of the node loop serves both harmonics (TORJ_HARM_RT)
 template <int M, int K>
-__device__ __forceinline__ void bessel_JD(double hz, double y, double& J, double& D) {
-    double sj = c_bess[M][K - 1], sd = c_bessd[M][K - 1];
+__device__ __forceinline__ void bessel_JD(double hz, double y, double& J, double& D, int m_rt = M) {
+    const int m = M ? M : m_rt;
+    double sj = c_bess[m][K - 1], sd = c_bessd[m][K - 1];
 #pragma unroll
     for (int k = K - 2; k >= 0; --k) {
-        sj = fma(sj, y, c_bess[M][k]);
-        sd = fma(sd, y, c_bessd[M][k]);
+        sj = fma(sj, y, c_bess[m][k]);
+        sd = fma(sd, y, c_bessd[m][k]);
     }
-    double p = (M == 2) ? hz * hz * 0.5 : hz * hz * hz * (1.0 / 6.0);
+    double p = (m == 2) ? hz * hz * 0.5 : hz * hz * hz * (1.0 / 6.0);
     J = p * sj;
     D = p * sd;
 }
@@ -488,7 +493,7 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
             D = 0.5 * z * (jn(m_rt - 1, z) - jn(m_rt + 1, z));
         } else {
             const double hz = 0.5 * z;
-            bessel_JD<M, K>(hz, hz * hz, J, D);
+            bessel_JD<M, K>(hz, hz * hz, J, D, m_rt);
         }
         const double J2 = J * J, JD = J * D;
         double pf = c.k1 * J2;                 // (|Axz|^2 + |ey|^2) J^2
@@ -506,9 +511,9 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
 
 // rarely taken variants kept out of line so the hot code stays small (instruction cache)
 template <int M>
-__device__ __noinline__ double harmonic_sum_large(const HarmCoef c) {  // by value: see eval_field_ext
-    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false>(c);
-    return harmonic_sum<M, 1, true>(c);
+__device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M) {  // by value: see eval_field_ext
+    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false>(c, m_rt);
+    return harmonic_sum<(M ? M : 2), 1, true>(c, m_rt);
 }
 
 // One harmonic's contribution to alpha [1/m] (sign included), or 0 when a rigorous bound shows it is < floor.
@@ -558,9 +563,9 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     }
     safe = false;
     cnt.n_harm++;
-    if (M == 0) return harmonic_sum<2, 1, true>(c, m);
-    if (c.x_m <= 3.2) return harmonic_sum<(M ? M : 2), 12, false>(c);
-    return harmonic_sum_large<(M ? M : 2)>(c);
+    if (M == 0 && m > 3) return harmonic_sum<2, 1, true>(c, m);
+    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false>(c, m);
+    return harmonic_sum_large<M>(c, m);
 }
 
 // Harmonics 4..max_harmonic (torj_options.max_harmonic > 3; the reference stops at 3, src/absorption.jl:199). Cold and
@@ -632,6 +637,16 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     h.floor_ = rc.alpha_floor;
     double alpha = 0.0;
     bool safe = rc.alpha_floor > 0.0;
+#if TORJ_HARM_RT
+    // one copy of the harmonic code for m = 2 and 3 (instruction-cache footprint), order chosen at run time
+#pragma unroll 1
+    for (int m = 2; m <= 3; ++m) {
+        if (m > rc.max_harmonic) break;
+        const double fm = (double)m;
+        if (fm >= m_0) alpha += harmonic_alpha<0>(h, cnt, safe, m);
+        else if (!(m_0 - fm > 0.02 * m_0)) safe = false;
+    }
+#else
     if (rc.max_harmonic >= 2) {
         if (2.0 >= m_0) alpha += harmonic_alpha<2>(h, cnt, safe);
         else if (!(m_0 - 2.0 > 0.02 * m_0)) safe = false;
@@ -640,6 +655,7 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
         if (3.0 >= m_0) alpha += harmonic_alpha<3>(h, cnt, safe);
         else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
     }
+#endif
     if (HIGH && rc.max_harmonic >= 4) {
         const HighHarm r = harmonics_above_3(h, rc.max_harmonic, m_0, safe);
         alpha += r.alpha; cnt.n_harm += r.n_harm; cnt.n_prune += r.n_prune; safe = r.safe;

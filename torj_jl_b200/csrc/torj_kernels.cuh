@@ -300,6 +300,10 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_ERR_INCR
 #define TORJ_ERR_INCR 0  // 1: accumulate the embedded error estimate stage by stage (7 more live registers per lane)
 #endif
+#ifndef TORJ_PARK
+#define TORJ_PARK 1  // 1: per-segment / per-ray scalars of the integrator live in shared memory
+#endif
+#define TORJ_PARK_SLOTS 9  // doubles per thread reserved when TORJ_PARK (7 doubles + 3 ints, rounded up)
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
@@ -357,24 +361,48 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     const double s_step = O.s_max / (double)O.n_segments;
 
     // per-lane ray state
+#if TORJ_PARK
+    // Scalars touched once per segment or per ray live in shared memory ([slot][thread], conflict-free): the kernel
+    // sits at the 255-register limit and the compiler, not knowing trip frequencies, otherwise spills values that
+    // every RHS evaluation touches (ray constants, counters) to local memory (122 -> 72 bytes of spills, -1 % time;
+    // parking the once-per-step scalars as well removes the spills altogether but gains nothing more).
+    double* pk = smem + a.n_psi + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + threadIdx.x;
+#define PK(k) pk[(k) * TORJ_TPB]
+    long long& ray = *reinterpret_cast<long long*>(&PK(0));
+    long long& tj = *reinterpret_cast<long long*>(&PK(1));  // index into the trajectory window or -1
+    double& s0 = PK(2);
+    double& dt0 = PK(3);
+    double& d1 = PK(4);
+    double& tot_dep = PK(5);
+    double& tot_w = PK(6);
+    int* pki = reinterpret_cast<int*>(pk + 7 * TORJ_TPB - threadIdx.x) + threadIdx.x;
+#define PKI(k) pki[(k) * TORJ_TPB]
+    int& seg = PKI(0);
+    int& last_stat = PKI(1);
+    unsigned int& rays_ok = *reinterpret_cast<unsigned int*>(&PKI(2));
+    ray = -1; tj = -1; s0 = 0.0; dt0 = 0.0; d1 = 0.0; tot_dep = 0.0; tot_w = 0.0; seg = 0; last_stat = 0; rays_ok = 0;
+#else
     long long ray = -1;
+    long long tj = -1;  // index into the trajectory window or -1
+    double s0 = 0.0, dt0 = 0.0, d1 = 0.0;
+    double tot_dep = 0.0, tot_w = 0.0;
+    int seg = 0, last_stat = 0;
+    unsigned int rays_ok = 0;
+#endif
     int phase = PH_IDLE, st = 0;
     bool exhausted = false;
     double u[7], tmp[7];
-    double s0 = 0.0, wgt = 0.0, pdep = 0.0;
-    double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0, dt0 = 0.0, d1 = 0.0;
+    double wgt = 0.0, pdep = 0.0;
+    double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0;
     double psi_cur = 0.0, dpsi_cur = 0.0, psi_new = 0.0, dpsi_new = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
 #if TORJ_ERR_INCR
     double err[7] = {0, 0, 0, 0, 0, 0, 0};
 #endif
-    int seg = 0, npts = 0, rstat = 0, nstep = 0, last_stat = 0;
+    int npts = 0, rstat = 0, nstep = 0;
     bool a_skip = false, a_skip_next = false;
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
-    double tot_dep = 0.0, tot_w = 0.0;
-    unsigned int rays_ok = 0;
-    long long tj = -1;  // index into the trajectory window or -1
 #pragma unroll
     for (int i = 0; i < 7; ++i) { u[i] = 0.0; tmp[i] = 0.0; }
 #pragma unroll
@@ -695,6 +723,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
     if (threadIdx.x < 8) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
 #undef KK
+#if TORJ_PARK
+#undef PK
+#undef PKI
+#endif
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
