@@ -27,29 +27,6 @@ namespace torj {
 #ifndef TORJ_ROW_FENCE
 #define TORJ_ROW_FENCE 1
 #endif
-#ifndef TORJ_EXP_ESTRIN
-#define TORJ_EXP_ESTRIN 0
-#endif
-#ifndef TORJ_HARM_RT
-#define TORJ_HARM_RT 0  // 1: harmonics 2 and 3 share one run-time-order copy of the quadrature code
-#endif
-#ifndef TORJ_NODE_UNROLL
-#define TORJ_NODE_UNROLL 1
-#endif
-#define TORJ_STR2(x) #x
-#define TORJ_STR(x) TORJ_STR2(x)
-#define TORJ_PRAGMA_NODE_UNROLL _Pragma(TORJ_STR(unroll TORJ_NODE_UNROLL))
-#ifndef TORJ_ROW_LOOP
-#define TORJ_ROW_LOOP 0
-#endif
-#ifndef TORJ_NOINLINE_MATH
-#define TORJ_NOINLINE_MATH 0  // 1: exp/rcp/rsqrt/sqrt helpers as shared subroutines (smaller hot loop)
-#endif
-#if TORJ_NOINLINE_MATH
-#define TORJ_MATH_INLINE __noinline__
-#else
-#define TORJ_MATH_INLINE __forceinline__
-#endif
 #define TORJ_BESS_K 24
 
 struct DevTables {
@@ -115,19 +92,19 @@ struct Counters {
 // RHS. Arguments here are normal, positive (or non-zero for rcp) numbers; zero is handled where it can occur
 // (sqrt_fast).
 // ------------------------------------------------------------------------------------------------
-__device__ TORJ_MATH_INLINE double rcp_fast(double x) {
+__device__ __forceinline__ double rcp_fast(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     const double e = fma(-x, r, 1.0);        // 1/x = r / (1 - e) = r (1 + e + e^2 + ...)
     return fma(r, fma(e, e, e), r);
 }
-__device__ TORJ_MATH_INLINE double rsqrt_fast(double x) {
+__device__ __forceinline__ double rsqrt_fast(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x * y, y, 1.0);    // x^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3 e^2/8 + ...)
     return fma(y, fma(0.375, e, 0.5) * e, y);
 }
-__device__ TORJ_MATH_INLINE double sqrt_fast(double x) {  // x >= 0
+__device__ __forceinline__ double sqrt_fast(double x) {  // x >= 0
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x * y, 0.5 * y, 0.5);
@@ -178,18 +155,9 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
     int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
     double v[4] = {0, 0, 0, 0}, vR[4] = {0, 0, 0, 0}, vZ[4] = {0, 0, 0, 0};
     double te = 0.0, ps = 0.0, psR = 0.0, psZ = 0.0;
-#if TORJ_ROW_LOOP
-    // rows as a real loop (4x less code for the 16-node stencil: the hot loop has to fit the instruction cache);
-    // the row weights are picked from registers with selects instead of indexing a local array
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const double wzj = j == 0 ? wz[0] : (j == 1 ? wz[1] : (j == 2 ? wz[2] : wz[3]));
-        const double dwzj = j == 0 ? dwz[0] : (j == 1 ? dwz[1] : (j == 2 ? dwz[2] : dwz[3]));
-#else
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const double wzj = wz[j], dwzj = dwz[j];
-#endif
         size_t node = (size_t)(bz + j) * T.row + br;
         const double2* pa = T.A + 2 * node;
         const double2* pb = T.B + node;
@@ -412,34 +380,15 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
 // scaled by 2^k built in the exponent field.
 __constant__ double c_exp[17];  // log2(e), -ln2_hi, -ln2_lo, 1/13!, 1/12!, ..., 1/2!, 1, 1 (constant-bank operands: a
                                 // 64-bit literal costs two extra issue slots per use, a c[][] operand none)
-__device__ TORJ_MATH_INLINE double exp_fast(double x) {
+__device__ __forceinline__ double exp_fast(double x) {
     x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
     x = x > 708.0 ? 708.0 : x;
     const double kd = rint(x * c_exp[0]);
     double r = fma(kd, c_exp[1], x);
     r = fma(kd, c_exp[2], r);
-#if TORJ_EXP_ESTRIN
-    // Estrin evaluation of sum_{n=0}^{13} r^n/n!: dependency depth 5 instead of 13 (DFMA latency is 8 cycles and
-    // only two warps share a scheduler). c_exp[16-n] = 1/n!.
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double q0 = fma(c_exp[15], r, c_exp[16]);   // 1 + r
-    const double q1 = fma(c_exp[13], r, c_exp[14]);   // 1/2! + r/3!
-    const double q2 = fma(c_exp[11], r, c_exp[12]);
-    const double q3 = fma(c_exp[9], r, c_exp[10]);
-    const double q4 = fma(c_exp[7], r, c_exp[8]);
-    const double q5 = fma(c_exp[5], r, c_exp[6]);
-    const double q6 = fma(c_exp[3], r, c_exp[4]);     // 1/12! + r/13!
-    const double s0 = fma(q1, r2, q0);                // degrees 0..3
-    const double s1 = fma(q3, r2, q2);                // 4..7
-    const double s2 = fma(q5, r2, q4);                // 8..11
-    const double t0 = fma(s1, r4, s0);                // 0..7
-    const double t1 = fma(q6, r4, s2);                // 8..13
-    const double p = fma(t1, r8, t0);
-#else
     double p = c_exp[3];
 #pragma unroll
     for (int i = 4; i < 17; ++i) p = fma(p, r, c_exp[i]);
-#endif
     const int k = (int)kd;  // in [-1022, 1022]
     return p * __hiloint2double((k + 1023) << 20, 0);
 }
@@ -449,7 +398,7 @@ __device__ TORJ_MATH_INLINE double exp_fast(double x) {
 // The reference's three Bessel functions enter abs_Al_pol_fact (src/absorption.jl:152-165) only through
 //   J_M^2,  J_M (J_{M-1} - J_{M+1}) = 2 J_M J_M',  J_{M-1} J_{M+1} = (M J_M / z)^2 - J_M'^2
 // so two series suffice and nothing is divided by z.
-// M = 0: order m_rt (2 or 3) chosen at run time — one copy of the node loop serves both harmonics (TORJ_HARM_RT)
+// M = 0: order m_rt chosen at run time (harmonics above the third; the one-copy-for-m-2-and-3 variant was slower)
 template <int M, int K>
 __device__ __forceinline__ void bessel_JD(double hz, double y, double& J, double& D, int m_rt = M) {
     const int m = M ? M : m_rt;
@@ -482,7 +431,7 @@ template <int M, int K, bool GENERIC>
 __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) {
     double sum = 0.0;
     const int n = c_gl.n;
-    TORJ_PRAGMA_NODE_UNROLL
+#pragma unroll 1
     for (int k = 0; k < n; ++k) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
         const double ex = exp_fast(fma(c.e1, t, c.e0));
@@ -637,16 +586,6 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     h.floor_ = rc.alpha_floor;
     double alpha = 0.0;
     bool safe = rc.alpha_floor > 0.0;
-#if TORJ_HARM_RT
-    // one copy of the harmonic code for m = 2 and 3 (instruction-cache footprint), order chosen at run time
-#pragma unroll 1
-    for (int m = 2; m <= 3; ++m) {
-        if (m > rc.max_harmonic) break;
-        const double fm = (double)m;
-        if (fm >= m_0) alpha += harmonic_alpha<0>(h, cnt, safe, m);
-        else if (!(m_0 - fm > 0.02 * m_0)) safe = false;
-    }
-#else
     if (rc.max_harmonic >= 2) {
         if (2.0 >= m_0) alpha += harmonic_alpha<2>(h, cnt, safe);
         else if (!(m_0 - 2.0 > 0.02 * m_0)) safe = false;
@@ -655,7 +594,6 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
         if (3.0 >= m_0) alpha += harmonic_alpha<3>(h, cnt, safe);
         else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
     }
-#endif
     if (HIGH && rc.max_harmonic >= 4) {
         const HighHarm r = harmonics_above_3(h, rc.max_harmonic, m_0, safe);
         alpha += r.alpha; cnt.n_harm += r.n_harm; cnt.n_prune += r.n_prune; safe = r.safe;

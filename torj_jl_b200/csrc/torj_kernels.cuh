@@ -294,12 +294,6 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_K_SMEM
 #define TORJ_K_SMEM 1  // 1: Runge-Kutta stage derivatives k[S][7] live in shared memory instead of (L1-backed) local memory
 #endif
-#ifndef TORJ_PSI_IN_RHS
-#define TORJ_PSI_IN_RHS 1  // 1: every RHS evaluation also returns psi_N and its arc-length derivative (no extra loads)
-#endif
-#ifndef TORJ_ERR_INCR
-#define TORJ_ERR_INCR 0  // 1: accumulate the embedded error estimate stage by stage (7 more live registers per lane)
-#endif
 #ifndef TORJ_PARK
 #define TORJ_PARK 1  // 1: per-segment / per-ray scalars of the integrator live in shared memory
 #endif
@@ -395,9 +389,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     double wgt = 0.0, pdep = 0.0;
     double t = 0.0, tstop = 0.0, dt = 0.0, qold = qoldinit, dtnew = 0.0;
     double psi_cur = 0.0, dpsi_cur = 0.0, psi_new = 0.0, dpsi_new = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
-#if TORJ_ERR_INCR
-    double err[7] = {0, 0, 0, 0, 0, 0, 0};
-#endif
     int npts = 0, rstat = 0, nstep = 0;
     bool a_skip = false, a_skip_next = false;
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
@@ -480,17 +471,9 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // with a 1e10 margin (abs_albajar)
         if (phase != PH_IDLE) {
             const bool inner = (phase == PH_STAGE && st < S - 1);
-            rhs<true, TORJ_PSI_IN_RHS != 0, HIGH>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
+            rhs<true, true, HIGH>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
             if (!inner) a_skip = a_skip_next;
         }
-#if !TORJ_PSI_IN_RHS
-        auto psi_here = [&](const double* xx, const double* dir) {  // psi_N and grad(psi_N).dx/ds at xx
-            double R = sqrt(xx[0] * xx[0] + xx[1] * xx[1]), pR, pZ;
-            eval_psi(T, R, xx[2], &out[7], &pR, &pZ);
-            out[8] = pR * (xx[0] * dir[0] + xx[1] * dir[1]) / R + pZ * dir[2];
-        };
-        if (phase == PH_SEED || phase == PH_CALLBACK || (phase == PH_STAGE && st == S - 1)) psi_here(tmp, out);
-#endif
 
         // ---- phase bookkeeping
         int act = ACT_NONE;
@@ -529,9 +512,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
                     KK(st, i) = out[i];
-#if TORJ_ERR_INCR
-                    err[i] = fma(bj, out[i], err[i]);
-#endif
                 }
             }
             if (st < S - 1) {
@@ -556,14 +536,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
-#if TORJ_ERR_INCR
-                    const double ut = err[i] * dt;
-#else
                     double ut = 0.0;
 #pragma unroll
                     for (int j = 0; j < S; ++j) ut = fma(s_bt[j], KK(j, i), ut);
                     ut *= dt;
-#endif
                     const double au = fabs(u[i]), an = fabs(tmp[i]);
                     at[i] = ut * rcp_fast(O.abstol + (au > an ? au : an) * O.reltol);
                     if (!(tmp[i] == tmp[i])) bad = true;
@@ -640,9 +616,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     for (int i = 0; i < 7; ++i) {
                         const double k0 = KK(0, i);
                         tmp[i] = fma(a10, k0, u[i]);
-#if TORJ_ERR_INCR
-                        err[i] = b0 * k0;
-#endif
                     }
                 }
                 phase = PH_STAGE;
