@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--workload", default="beam64k", choices=["beam64k", "sweep1m"],
                     help="beam64k: configs[2], weak scaling (default); sweep1m: configs[3], 1 049 600 rays, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--schedule", type=int, default=0, choices=[0, 1, 2],
+                    help="torj_options.schedule: 0 automatic (default), 1 whole rays per lane, 2 segment hand-off")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -192,7 +194,7 @@ def main():
     n = len(w)
     psi = np.ascontiguousarray(np.linspace(0.0, 1.0, WORKLOAD["n_psi"]))
     n_psi = len(psi)
-    opt = _lib.default_options()
+    opt = _lib.default_options(schedule=args.schedule)
     dp = lambda a: a.ctypes.data_as(_lib.c_dp)
 
     # ---- resident bundle: inputs in HBM before the timed region ("value")
@@ -245,7 +247,7 @@ def main():
 
     # ---- end to end through the reference-facing call with HOST buffers (H2D of the bundle, D2H of the results)
     def e2e_step():
-        r = tj.trace_bundle(pl, pos, dirs, w, WORKLOAD["f"], WORKLOAD["mode"], WORKLOAD["s_max"], psi, ctx=ctx)
+        r = tj.trace_bundle(pl, pos, dirs, w, WORKLOAD["f"], WORKLOAD["mode"], WORKLOAD["s_max"], psi, ctx=ctx, options=opt)
         if world > 1:
             t = torch.from_numpy(np.concatenate([r["dP_dV"], [r["deposited_power"], w.sum()]])).cuda()
             dist.all_reduce(t)
@@ -291,7 +293,7 @@ def main():
                 "config": {"workload": "config4_1M_ray_angle_sweep" if args.workload == "sweep1m" else
                            ("config2_1k_ray_beam" if args.small else WORKLOAD["name"]), "n_rays_per_gpu": n,
                            "grid": WORKLOAD["grid"], "s_max": WORKLOAD["s_max"], "n_psi": n_psi, "f": WORKLOAD["f"],
-                           "mode": WORKLOAD["mode"], "scheme": "Tsit5", "l2": "compute-bound kernel; tables 4.8 MB resident, "
+                           "mode": WORKLOAD["mode"], "scheme": "Tsit5", "schedule": args.schedule, "l2": "compute-bound kernel; tables 4.8 MB resident, "
                            "no L2 flush needed (inputs are re-read from HBM each step: ray state 7.3 MB)"},
                 "rays_per_s": rays_all / (ms_per_step * 1e-3), "rays_total": int(rays_all), "rays_ok": int(rays_ok.item()),
                 "e2e": {"value": steps_all / (e2e_ms * 1e-3), "unit": "ray-steps/s", "h2d_bytes_per_step": h2d,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TORJ_ABI_VERSION 1
+#define TORJ_ABI_VERSION 2
 
 typedef struct torj_ctx torj_ctx;       /* one per (process, device): stream, quadrature nodes, launch counter */
 typedef struct torj_plasma torj_plasma; /* device-resident equilibrium tables (reference struct Plasma, src/plasma.jl:2-14) */
@@ -61,6 +61,12 @@ typedef struct torj_options {
                                       upper bound of its contribution to alpha is below this (|J_n|<=1, sum of weights 2,
                                       max exponent on the resonance curve); optical-depth error <= 2*alpha_floor*path.
                                       0 = evaluate every integral exactly as the reference does */
+    int32_t schedule;              /* how rays are mapped to GPU lanes; results do not depend on it.
+                                      0 = automatic; 1 = a lane keeps a ray from entry to retirement;
+                                      2 = segment hand-off: a ray may change lanes between two of its n_segments
+                                      segments, so all rays advance together and a bundle of 1..16 times the resident
+                                      lanes does not end with a partly filled last wave (automatic picks this there) */
+    int32_t reserved_;             /* keeps the struct size a multiple of 8; must be 0 */
 } torj_options;
 
 typedef struct torj_counters {

@@ -11,6 +11,7 @@ struct TorjOptions          # torj_options, field for field
     dtmax::Float64; abstol::Float64; reltol::Float64; psi_stop::Float64; p_stop::Float64; te_min::Float64
     max_harmonic::Int32; max_steps_per_segment::Int32
     alpha_floor::Float64
+    schedule::Int32; reserved_::Int32
 end
 struct TorjGrid; nR::Int32; nZ::Int32; R_first::Float64; R_last::Float64; Z_first::Float64; Z_last::Float64; end
 struct TorjCounters; n_acc::Int64; n_rej::Int64; n_rhs::Int64; n_alpha::Int64; n_harm::Int64; n_rays_ok::Int64; n_harm_pruned::Int64; n_alpha_skipped::Int64; end

@@ -420,10 +420,39 @@ def test_harmonics_above_the_third(gl24):
     assert 0.5 < absorbed[4] < absorbed[5] < 1.0 + 1e-12
 
 
+def test_segment_handoff_schedule_gives_the_same_rays(gpu_small, arrays_small, launcher):
+    """torj_options.schedule: 2 = a ray changes lanes (and SMs) between segments, its state travelling through global
+    memory; 1 = a lane keeps its ray. Per-ray results must be IDENTICAL (same arithmetic in the same order); the
+    profile differs only by the order of the atomic adds. Covers failing rays, a trajectory window and two beams."""
+    L = launcher
+    pos, dirs, w = tj.launch_peripheral_rays(L["x0"], L["N0"], L["spot"], L["inv_Rc"], L["f"],
+                                             N_rings=4, min_azimuthal_points=7)
+    n = len(w)
+    pos = pos.copy(); pos[3] = [9.0, 0.0, 0.0]; pos[7] = [2.5, 0.0, 3.0]       # two rays that never reach the plasma
+    f = np.where(np.arange(n) % 2 == 0, 95e9, 110e9); mode = np.where(np.arange(n) % 3 == 0, -1, 1)
+    beam = (np.arange(n) % 2).astype(np.int32)
+    psi = np.linspace(0, 1, 80)
+    out = {}
+    for sched in (1, 2):
+        out[sched] = tj.trace_bundle(gpu_small, pos, dirs, w, f, mode, 0.6, psi, options=tj.default_options(schedule=sched, n_segments=30),
+                                     trajectories=(0, n), traj_max_pts=2 + 30 * 210, beam_id=beam, n_beams=2)
+    a, b = out[1], out[2]
+    assert np.array_equal(a["status"], b["status"]) and (a["status"] != 0).sum() == 2
+    ok = a["status"] == 0
+    assert np.array_equal(a["n_points"], b["n_points"])
+    assert np.array_equal(a["P_final"][ok], b["P_final"][ok])
+    assert np.array_equal(a["P_deposited_ray"], b["P_deposited_ray"])
+    for k in ("traj_s", "traj_xyz", "traj_P", "traj_dP_ds", "traj_dP_dV_ray"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["dP_dV"].shape == (2, 80) and l2rel(b["dP_dV"].ravel(), a["dP_dV"].ravel()) < 1e-13
+    assert np.allclose(a["deposited_power"], b["deposited_power"], rtol=1e-13, atol=0)
+    assert a["counters"]["n_acc"] == b["counters"]["n_acc"] and a["counters"]["n_rhs"] == b["counters"]["n_rhs"]
+
+
 def test_option_validation(gpu_small, launcher):
     psi = np.linspace(0, 1, 10)
     for bad in (dict(max_harmonic=0), dict(max_harmonic=17), dict(scheme=2), dict(n_segments=0), dict(dtmax=0.0),
-                dict(abstol=-1.0), dict(alpha_floor=-1.0), dict(max_steps_per_segment=0)):
+                dict(abstol=-1.0), dict(alpha_floor=-1.0), dict(max_steps_per_segment=0), dict(schedule=3)):
         with pytest.raises(tj.TorjError):
             tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, psi,
                             options=tj.default_options(**bad))

@@ -18,7 +18,8 @@ class TorjOptions(C.Structure):
     """torj_options: solver constants the reference hard-codes (src/solve.jl:145,157,174,176; src/absorption.jl:194,199)."""
     _fields_ = [("scheme", C.c_int32), ("n_segments", C.c_int32), ("dtmax", C.c_double), ("abstol", C.c_double),
                 ("reltol", C.c_double), ("psi_stop", C.c_double), ("p_stop", C.c_double), ("te_min", C.c_double),
-                ("max_harmonic", C.c_int32), ("max_steps_per_segment", C.c_int32), ("alpha_floor", C.c_double)]
+                ("max_harmonic", C.c_int32), ("max_steps_per_segment", C.c_int32), ("alpha_floor", C.c_double),
+                ("schedule", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TorjCounters(C.Structure):

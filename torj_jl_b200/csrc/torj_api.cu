@@ -69,6 +69,9 @@ struct torj_bundle {
     int n_psi = 0;
     double *d_edges = nullptr, *d_bins = nullptr, *d_dV = nullptr, *d_profile = nullptr;
     unsigned long long *d_queue = nullptr, *d_counters = nullptr;
+    // segment hand-off (allocated on first use)
+    double* d_hand = nullptr;
+    int *d_segdone = nullptr, *d_left = nullptr;
     // trajectory window
     int64_t traj_first = 0, traj_count = 0;
     int traj_max = 0;
@@ -102,6 +105,8 @@ void torj_options_default(torj_options* o) {
     o->p_stop = 1e-6;
     o->te_min = 20.0;
     o->max_harmonic = 3;
+    o->schedule = 0;
+    o->reserved_ = 0;
     o->max_steps_per_segment = 100000;
     o->alpha_floor = 1e-14;
 }
@@ -642,6 +647,7 @@ void torj_bundle_destroy(torj_bundle* b) {
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->d_pos); cudaFree(b->d_dir); cudaFree(b->d_w); cudaFree(b->d_freq); cudaFree(b->d_mode); cudaFree(b->d_u0);
     cudaFree(b->d_s0); cudaFree(b->d_psil); cudaFree(b->d_Pf); cudaFree(b->d_Pdep); cudaFree(b->d_status); cudaFree(b->d_npts);
+    cudaFree(b->d_hand); cudaFree(b->d_segdone); cudaFree(b->d_left);
     cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
     cudaFree(b->d_profile);
     cudaFree(b->d_beam);
@@ -695,6 +701,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
     if (od.max_harmonic < 1 || od.max_harmonic > 16) FAIL("torj_bundle_trace: max_harmonic must be in 1..16 (1 = no absorption)");
     if (!(od.dtmax > 0.0) || !(od.abstol > 0.0) || !(od.reltol > 0.0)) FAIL("torj_bundle_trace: dtmax, abstol and reltol must be > 0");
+    if (od.schedule < 0 || od.schedule > 2) FAIL("torj_bundle_trace: schedule must be 0 (automatic), 1 (whole rays) or 2 (segment hand-off)");
     if (od.max_steps_per_segment < 1) FAIL("torj_bundle_trace: max_steps_per_segment < 1");
     if (!(s_max > 0.0)) FAIL("torj_bundle_trace: s_max must be > 0");
     if (set_device(c)) return 1;
@@ -758,6 +765,25 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TORJ_TPB, smem));
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
     int64_t grid = std::min<int64_t>((int64_t)c->num_sms * bps, blocks_needed);  // persistent: resident CTAs only
+    // Segment hand-off when the bundle is a few times the resident lanes: without it the last wave of rays runs on
+    // partly empty SMs (65 543 rays on 37 888 lanes: two ray-times instead of 1.73). Below one wave there is nothing to
+    // balance, far above it the last wave no longer matters.
+    const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB;
+    int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes && b->n <= 16 * lanes);
+    if (od.n_segments < 2) interleave = 0;
+    a.interleave = interleave; a.hand = nullptr; a.seg_done = nullptr; a.rays_left = nullptr;
+    if (interleave) {
+        if (!b->d_hand) {
+            CK(cudaMalloc(&b->d_hand, (size_t)b->n * TORJ_HAND_D * sizeof(double)));
+            CK(cudaMalloc(&b->d_segdone, (size_t)b->n * sizeof(int)));
+            CK(cudaMalloc(&b->d_left, sizeof(int)));
+        }
+        const int left = (int)b->n;
+        CK(cudaMemsetAsync(b->d_segdone, 0, (size_t)b->n * sizeof(int), st));
+        CK(cudaMemcpyAsync(b->d_left, &left, sizeof left, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // `left` is a local
+        a.hand = b->d_hand; a.seg_done = b->d_segdone; a.rays_left = b->d_left;
+    }
     CK(cudaEventRecord(c->ev0, st));
     kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
     c->launches++;

@@ -34,7 +34,7 @@ struct BundleDev {
     double* u0;            // [7][n] state at plasma entry
     double* s0;            // [n] vacuum path length
     double* psi_launch;    // [n]
-    int* status;           // [n]
+    int* status;           // [n] written by k_ray_init (rays with status != 0 are never traced), then by k_trace at retirement
     double* P_final;       // [n]
     double* P_dep;         // [n] profile-integrated deposited power of the ray
     int* n_points;         // [n]
@@ -265,7 +265,15 @@ struct TraceArgs {
     double* bins;                     // [n_beams][n_psi+2]: weighted shell power, then sum w_i P_i and sum w_i
     unsigned long long* next_ray;     // work queue head
     unsigned long long* counters;     // n_acc, n_rej, n_rhs, n_alpha, n_harm, n_rays_ok, n_prune, n_askip
+    // segment hand-off (interleave = 1): work item i is segment i / n of ray i % n; a ray changes lanes between
+    // segments, so all rays advance together and the bundle ends after n/lanes ray-times instead of ceil(n/lanes)
+    int interleave;
+    double* hand;                     // [n][TORJ_HAND_D] ray state between two segments
+    int* seg_done;                    // [n] segments completed; TORJ_SEG_RETIRED once the ray has ended
+    int* rays_left;                   // rays not yet retired
 };
+#define TORJ_HAND_D 20
+#define TORJ_SEG_RETIRED 0x7fffffff
 
 __device__ __forceinline__ double eps_of(double x) {  // Julia eps(x)
     x = fabs(x);
@@ -307,7 +315,9 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 // Integrator phases. Every trip of the kernel's main loop evaluates the RHS exactly once per lane that holds a
 // ray, whatever that lane's phase, so the expensive code is always warp-converged; the cheap phase-specific
 // bookkeeping after it is the only divergent part. A lane that retires its ray draws a new one on the next trip.
-enum { PH_IDLE = 0, PH_SEED = 1, PH_INITDT = 2, PH_STAGE = 3, PH_CALLBACK = 4 };
+// PH_WAIT / PH_RESUME (segment hand-off only): the lane holds a work item whose previous segment is still running on
+// another lane / has just loaded a ray's state. Phases >= PH_SEED evaluate the RHS.
+enum { PH_IDLE = 0, PH_WAIT = 1, PH_RESUME = 2, PH_SEED = 3, PH_INITDT = 4, PH_STAGE = 5, PH_CALLBACK = 6 };
 enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT = 3, ACT_AFTER_ACCEPT = 4 };
 
 #ifdef TORJ_MAXNREG
@@ -391,6 +401,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     double psi_cur = 0.0, dpsi_cur = 0.0, psi_new = 0.0, dpsi_new = 0.0, P_a = 1.0, dP_a = 0.0, hstep = 0.0;
     int npts = 0, rstat = 0, nstep = 0;
     bool a_skip = false, a_skip_next = false;
+    int wseg = 0;  // segment index of the work item held (segment hand-off)
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
     Counters cnt = {0, 0, 0, 0, 0, 0, 0};
@@ -406,7 +417,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         if (a.n_beams > 1) atomicAdd(&beam_bins[shell], wgt * dP);
         else atomicAdd(&s_bins[shell], wgt * dP);
         pdep += dP;
-        if (tj >= 0) a.J.prof[tj * n_psi + shell] += dP;
+        if (tj >= 0) atomicAdd(&a.J.prof[tj * n_psi + shell], dP);  // (a ray may change SMs between segments)
     };
     auto put_point = [&](double s, const double* xx, double P, double dP) {
         if (tj >= 0) {
@@ -422,43 +433,121 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         npts++;
     };
 
+    // per-ray constants of the lane (both at the first pick-up of a ray and when a hand-off state is loaded)
+    auto bind_ray = [&](long long idx) {
+        ray = idx;
+        s0 = a.B.s0[idx];
+        wgt = a.B.weight[idx];
+        double f = a.B.per_ray_fm ? a.B.freq[idx] : a.B.freq[0];
+        int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
+        rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
+        if (a.n_beams > 1) beam_bins = a.bins + (size_t)a.beam_id[idx] * (n_psi + 2);
+        if (TORJ_FATAL(last_stat)) {  // a dead ray may have left NaN/Inf in the stage slots (0 * NaN != 0)
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+#pragma unroll
+                for (int i = 0; i < 7; ++i) KK(j, i) = 0.0;
+            last_stat = 0;
+        }
+        tj = (idx >= a.J.first && idx < a.J.first + a.J.count) ? idx - a.J.first : -1;
+    };
+    auto start_ray = [&](long long idx) {
+        bind_ray(idx);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { u[i] = a.B.u0[(size_t)i * n + idx]; tmp[i] = u[i]; }
+        seg = 0; npts = 0; rstat = 0; pdep = 0.0;
+        // samples 1 and 2: launch point and plasma entry (reference src/solve.jl:149-153)
+        double xl[3] = {a.B.pos[idx], a.B.pos[n + idx], a.B.pos[2 * n + idx]};
+        put_point(0.0, xl, 1.0, 0.0);
+        put_point(s0, u, 1.0, 0.0);
+        phase = PH_SEED;
+        a_skip = false;
+    };
+    // segment hand-off: the state a ray carries from one segment to the next (L2-coherent accesses: another SM wrote it)
+    auto save_ray = [&]() {
+        double2* h = reinterpret_cast<double2*>(a.hand + (size_t)ray * TORJ_HAND_D);
+        __stcg(h + 0, make_double2(u[0], u[1])); __stcg(h + 1, make_double2(u[2], u[3]));
+        __stcg(h + 2, make_double2(u[4], u[5])); __stcg(h + 3, make_double2(u[6], KK(0, 0)));
+        __stcg(h + 4, make_double2(KK(0, 1), KK(0, 2))); __stcg(h + 5, make_double2(KK(0, 3), KK(0, 4)));
+        __stcg(h + 6, make_double2(KK(0, 5), KK(0, 6))); __stcg(h + 7, make_double2(psi_cur, dpsi_cur));
+        __stcg(h + 8, make_double2(dst.P_last, pdep));
+        __stcg(h + 9, make_double2(__hiloint2double(dst.shell, dst.valid), __hiloint2double(npts, rstat | (a_skip ? 256 : 0))));
+        __threadfence();
+        atomicExch(&a.seg_done[ray], seg);
+    };
+    auto load_ray = [&](long long idx) {
+        bind_ray(idx);
+        const double2* h = reinterpret_cast<const double2*>(a.hand + (size_t)idx * TORJ_HAND_D);
+        double2 q;
+        q = __ldcg(h + 0); u[0] = q.x; u[1] = q.y;
+        q = __ldcg(h + 1); u[2] = q.x; u[3] = q.y;
+        q = __ldcg(h + 2); u[4] = q.x; u[5] = q.y;
+        q = __ldcg(h + 3); u[6] = q.x; KK(0, 0) = q.y;
+        q = __ldcg(h + 4); KK(0, 1) = q.x; KK(0, 2) = q.y;
+        q = __ldcg(h + 5); KK(0, 3) = q.x; KK(0, 4) = q.y;
+        q = __ldcg(h + 6); KK(0, 5) = q.x; KK(0, 6) = q.y;
+        q = __ldcg(h + 7); psi_cur = q.x; dpsi_cur = q.y;
+        q = __ldcg(h + 8); dst.P_last = q.x; pdep = q.y;
+        q = __ldcg(h + 9);
+        dst.shell = __double2hiint(q.x); dst.valid = __double2loint(q.x);
+        npts = __double2hiint(q.y);
+        const int fl = __double2loint(q.y);
+        rstat = fl & 255; a_skip = (fl & 256) != 0;
+        seg = wseg;
+        phase = PH_RESUME;
+    };
+    // try to start the held item (ray idx, segment wseg): possible once the ray's previous segment has been handed in
+    auto claim = [&](long long idx) {
+        ray = idx;
+        const int d = atomicAdd(&a.seg_done[idx], 0);
+        if (d == TORJ_SEG_RETIRED) {
+            phase = PH_IDLE; ray = -1;
+        } else if (d == wseg) {
+            __threadfence();
+            if (wseg > 0) {
+                load_ray(idx);
+            } else if (a.B.status[idx] == 0) {
+                start_ray(idx);
+            } else {  // failed initialisation (k_ray_init): retire at once
+                atomicExch(&a.seg_done[idx], TORJ_SEG_RETIRED);
+                atomicSub(a.rays_left, 1);
+                phase = PH_IDLE; ray = -1;
+            }
+        } else {
+            phase = PH_WAIT;
+        }
+    };
+
     for (;;) {
-        // ---- warp-ballot retire-and-refill: idle lanes draw the next ray indices from the global queue
+        // ---- warp-ballot retire-and-refill: idle lanes draw the next work items from the global queue
+        if (a.interleave && phase == PH_WAIT) claim(ray);
         unsigned need = __ballot_sync(FULL, phase == PH_IDLE && !exhausted);
         if (need) {
             int leader = __ffs(need) - 1;
             unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(a.next_ray, (unsigned long long)__popc(need));
+            int left = 1;
+            if ((int)lane == leader) {
+                base = atomicAdd(a.next_ray, (unsigned long long)__popc(need));
+                if (a.interleave) left = atomicAdd(a.rays_left, 0);
+            }
             base = __shfl_sync(FULL, base, leader);
+            left = __shfl_sync(FULL, left, leader);
             if (phase == PH_IDLE && !exhausted) {
                 long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
-                if (idx >= n) {
-                    exhausted = true;
-                } else if (a.B.status[idx] == 0) {  // failed initialisations were reported by k_ray_init
-                    ray = idx;
-#pragma unroll
-                    for (int i = 0; i < 7; ++i) { u[i] = a.B.u0[(size_t)i * n + idx]; tmp[i] = u[i]; }
-                    s0 = a.B.s0[idx];
-                    wgt = a.B.weight[idx];
-                    double f = a.B.per_ray_fm ? a.B.freq[idx] : a.B.freq[0];
-                    int mode = a.B.per_ray_fm ? a.B.mode[idx] : a.B.mode[0];
-                    rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
-                    seg = 0; npts = 0; rstat = 0; pdep = 0.0;
-                    if (a.n_beams > 1) beam_bins = a.bins + (size_t)a.beam_id[idx] * (n_psi + 2);
-                    if (TORJ_FATAL(last_stat)) {  // a dead ray may have left NaN/Inf in the stage slots (0 * NaN != 0)
-#pragma unroll
-                        for (int j = 0; j < S; ++j)
-#pragma unroll
-                            for (int i = 0; i < 7; ++i) KK(j, i) = 0.0;
-                        last_stat = 0;
+                if (!a.interleave) {
+                    if (idx >= n) {
+                        exhausted = true;
+                    } else if (a.B.status[idx] == 0) {  // failed initialisations were reported by k_ray_init
+                        start_ray(idx);
                     }
-                    tj = (idx >= a.J.first && idx < a.J.first + a.J.count) ? idx - a.J.first : -1;
-                    // samples 1 and 2: launch point and plasma entry (reference src/solve.jl:149-153)
-                    double xl[3] = {a.B.pos[idx], a.B.pos[n + idx], a.B.pos[2 * n + idx]};
-                    put_point(0.0, xl, 1.0, 0.0);
-                    put_point(s0, u, 1.0, 0.0);
-                    phase = PH_SEED;
-                    a_skip = false;
+                } else {
+                    // item idx = segment idx / n of ray idx % n; items of retired rays are void
+                    if (left == 0 || idx >= n * (long long)O.n_segments) {
+                        exhausted = true;
+                    } else {
+                        wseg = (int)(idx / n);
+                        claim(idx - (long long)wseg * n);
+                    }
                 }
             }
         }
@@ -469,7 +558,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // alpha is evaluated in full at the FSAL stage (= first stage of the next step) and in the seed / callback /
         // initial-dt phases; the inner stages take alpha = 0 when that evaluation found every harmonic negligible
         // with a 1e10 margin (abs_albajar)
-        if (phase != PH_IDLE) {
+        if (phase >= PH_SEED) {
             const bool inner = (phase == PH_STAGE && st < S - 1);
             rhs<true, true, HIGH>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
             if (!inner) a_skip = a_skip_next;
@@ -594,6 +683,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             psi_new = out[7];
             dpsi_new = out[8];
             act = ACT_AFTER_ACCEPT;
+        } else if (phase == PH_RESUME) {
+            act = ACT_BEGIN_SEGMENT;
         }
 
         // ---- transitions that need no RHS evaluation
@@ -639,6 +730,15 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                         }
                         rays_ok++;
                     }
+                    if (a.interleave) {
+                        atomicExch(&a.seg_done[ray], TORJ_SEG_RETIRED);
+                        atomicSub(a.rays_left, 1);
+                    }
+                    ray = -1;
+                    phase = PH_IDLE;
+                    act = ACT_NONE;
+                } else if (a.interleave) {
+                    save_ray();  // the next segment is a separate work item, usually taken by another lane
                     ray = -1;
                     phase = PH_IDLE;
                     act = ACT_NONE;
