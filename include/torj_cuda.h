@@ -64,8 +64,9 @@ typedef struct torj_options {
     int32_t schedule;              /* how rays are mapped to GPU lanes; results do not depend on it.
                                       0 = automatic; 1 = a lane keeps a ray from entry to retirement;
                                       2 = segment hand-off: a ray may change lanes between two of its n_segments
-                                      segments, so all rays advance together and a bundle of 1..16 times the resident
-                                      lanes does not end with a partly filled last wave (automatic picks this there) */
+                                      segments, so all rays advance together: no partly filled last wave, and the lanes
+                                      of a warp stay in step (automatic picks this when the bundle exceeds the resident
+                                      lanes, 37 888 on a B200) */
     int32_t reserved_;             /* keeps the struct size a multiple of 8; must be 0 */
 } torj_options;
 

@@ -765,11 +765,12 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TORJ_TPB, smem));
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
     int64_t grid = std::min<int64_t>((int64_t)c->num_sms * bps, blocks_needed);  // persistent: resident CTAs only
-    // Segment hand-off when the bundle is a few times the resident lanes: without it the last wave of rays runs on
-    // partly empty SMs (65 543 rays on 37 888 lanes: two ray-times instead of 1.73). Below one wave there is nothing to
-    // balance, far above it the last wave no longer matters.
+    // Segment hand-off whenever the bundle exceeds the resident lanes. It removes the partly filled last wave (65 543
+    // rays on 37 888 lanes: 1.73 ray-times instead of 2) and keeps the lanes of a warp in step: with whole rays per lane
+    // a bundle of rays of very different lengths (the 1 M-ray angle sweep) drifts apart and some lane pays for the full
+    // absorption coefficient on every trip (measured 3.1 s -> 2.4 s). Below one wave there is nothing to balance.
     const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB;
-    int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes && b->n <= 16 * lanes);
+    int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes);
     if (od.n_segments < 2) interleave = 0;
     a.interleave = interleave; a.hand = nullptr; a.seg_done = nullptr; a.rays_left = nullptr;
     if (interleave) {
