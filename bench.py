@@ -47,9 +47,10 @@ def bundle_for_rank(rank, small=False):
 
 def sweep_bundle(rank, world):
     """BASELINE.json configs[3]: 32 x 32 launcher angles (pol 10..40 deg, tor -15..15 deg) x 1 025-ray beams =
-    1 049 600 rays, sharded by contiguous ray blocks over the ranks (strong scaling)."""
+    1 049 600 rays; the 1 024 beams are dealt round-robin to the ranks (strong scaling; contiguous blocks would give
+    every rank a different range of launcher angles, i.e. rays of different lengths)."""
     import torj_jl_b200 as tj
-    from torj_jl_b200.distributed import shard_range
+    from torj_jl_b200.distributed import shard_block_cyclic
     x0 = np.array([2.5, 0.0, 0.4])
     P, D, W = [], [], []
     for pol in np.deg2rad(np.linspace(10.0, 40.0, 32)):
@@ -58,8 +59,8 @@ def sweep_bundle(rank, world):
                                                 N_rings=7, min_azimuthal_points=20)
             P.append(p); D.append(d); W.append(w / 1024.0)
     P, D, W = np.concatenate(P), np.concatenate(D), np.concatenate(W)
-    lo, hi = shard_range(len(W), rank, world)
-    return P[lo:hi], D[lo:hi], W[lo:hi], len(W)
+    idx = shard_block_cyclic(len(W), 1025, rank, world)
+    return P[idx], D[idx], W[idx], len(W)
 
 
 def ncu_traffic():

@@ -130,3 +130,14 @@ def test_prefilter_helpers_match_scipy():
         yy = rng.normal(size=n); cc = np.empty(n + 2)
         _lib.check(tj.lib().torj_bspline_prefilter_1d(n, yy.ctypes.data_as(_lib.c_dp), cc.ctypes.data_as(_lib.c_dp)))
         assert np.abs(_eval_1d_line(cc, 0.0, 1.0, n, np.arange(n * 1.0)) - yy).max() < 1e-14
+
+
+def test_block_cyclic_sharding_partitions_the_rays():
+    from torj_jl_b200.distributed import shard_block_cyclic
+    for n, block, world in ((1049600, 1025, 8), (10, 3, 4), (7, 7, 2), (100, 1, 3)):
+        parts = [shard_block_cyclic(n, block, r, world) for r in range(world)]
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(n))
+        assert all(np.all(np.diff(p) > 0) for p in parts if len(p) > 1)
+    p = shard_block_cyclic(1049600, 1025, 3, 8)
+    assert p[0] == 3 * 1025 and p[1025] == 11 * 1025 and len(p) == 128 * 1025

@@ -523,8 +523,9 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // ---- warp-ballot retire-and-refill: idle lanes draw the next work items from the global queue.
         // With segment hand-off a segment starts only on every (S-1)-th trip of the warp: a step is S-1 trips, so the
         // FSAL stages — the only ones that evaluate alpha in full — of all lanes of a warp fall on the same trips for
-        // good, instead of some lane paying for alpha on every trip (-2.8 % on both bench workloads; up to 4 idle trips
-        // per 600-trip segment).
+        // good, instead of some lane paying for alpha on every trip (-2.8 % on both bench workloads).
+        // (Restarting the cadence whenever no lane of the warp is inside a segment would save the in-step lanes their
+        // <= 4 idle trips per segment, but measured +1.5 %: the fixed cadence is also what regroups stragglers.)
         const bool aligned = (cadence == 0);
         cadence = (cadence + 1 == S - 1) ? 0 : cadence + 1;
         if (a.interleave && phase == PH_WAIT) claim(ray, aligned);
