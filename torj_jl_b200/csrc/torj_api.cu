@@ -2,8 +2,10 @@
 // Plain CUDA runtime; no torch types, no CPU fallback (every entry point needs a CUDA device).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <memory>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -41,7 +43,7 @@ struct torj_ctx {
     struct torj_bundle* ws = nullptr;  // workspace of the one-shot torj_trace call, kept between calls
 };
 
-static uint64_t g_plasma_serial = 0;
+static std::atomic<uint64_t> g_plasma_serial{0};  // torj_multi_* creates plasmas from one host thread per device
 
 struct torj_plasma {
     torj_ctx* ctx = nullptr;
@@ -72,6 +74,7 @@ struct torj_bundle {
     // segment hand-off (allocated on first use)
     double* d_hand = nullptr;
     int *d_segdone = nullptr, *d_left = nullptr;
+    int h_left = 0;  // source of the copy into d_left (outlives the call)
     // trajectory window
     int64_t traj_first = 0, traj_count = 0;
     int traj_max = 0;
@@ -83,6 +86,30 @@ struct torj_bundle {
     // beams
     int n_beams = 1, prof_rows = 0;
     int* d_beam = nullptr;
+};
+
+// Error paths: temporaries are owned by dev_ptr, objects under construction by a guard that destroys them unless the
+// function reaches its end (every CK / FAIL returns early).
+struct DevFree {
+    void operator()(void* p) const { cudaFree(p); }
+};
+template <class T>
+using dev_ptr = std::unique_ptr<T, DevFree>;
+template <class T>
+static cudaError_t dev_alloc(dev_ptr<T>& p, size_t count) {
+    T* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, count * sizeof(T));
+    p.reset(raw);
+    return e;
+}
+template <class T, void (*Destroy)(T*)>
+struct Guard {
+    T* p;
+    explicit Guard(T* q) : p(q) {}
+    ~Guard() { if (p) Destroy(p); }
+    T* release() { T* q = p; p = nullptr; return q; }
+    Guard(const Guard&) = delete;
+    Guard& operator=(const Guard&) = delete;
 };
 
 static int set_device(const torj_ctx* c) {
@@ -143,6 +170,7 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
     if (device < 0 || device >= ndev) FAIL("torj_ctx_create: bad device index");
     CK(cudaSetDevice(device));
     torj_ctx* c = new torj_ctx();
+    Guard<torj_ctx, torj_ctx_destroy> guard(c);
     c->device = device;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
@@ -174,7 +202,7 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
         for (int j = 0; j <= 13; ++j) ce[3 + j] = inv[13 - j];
         CK(cudaMemcpyToSymbol(c_exp, ce, sizeof ce));
     }
-    *out = c;
+    *out = guard.release();
     return 0;
 }
 
@@ -272,6 +300,7 @@ int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, 
     if (g->nR < 2 || g->nZ < 2 || n_vol < 2) FAIL("torj_plasma_create: grid too small");
     if (set_device(c)) return 1;
     torj_plasma* p = new torj_plasma();
+    Guard<torj_plasma, torj_plasma_destroy> guard(p);
     p->ctx = c;
     p->id = ++g_plasma_serial;
     size_t nodes = (size_t)(g->nR + 2) * (g->nZ + 2);
@@ -298,7 +327,7 @@ int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, 
     CK(cudaMemcpy(p->dT, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
     p->vol_c.assign(vol_coef, vol_coef + n_vol + 2);
     p->n_vol = n_vol; p->vol_x0 = vol_psi0; p->vol_h = vol_dpsi;
-    *out = p;
+    *out = guard.release();
     return 0;
 }
 
@@ -364,14 +393,16 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
     double psi_prof_max = psi_prof[0];
     for (int i = 1; i < n_prof; ++i) psi_prof_max = std::max(psi_prof_max, psi_prof[i]);
     // ---- device: node data of six fields, R pass, Z pass, pack
-    double *d_raw = nullptr, *d_tmp = nullptr, *d_coef = nullptr, *d_c1 = nullptr, *d_cpR = nullptr, *d_cpZ = nullptr;
-    CK(cudaMalloc(&d_raw, 6 * npts * sizeof(double)));
-    CK(cudaMalloc(&d_tmp, (size_t)sr * nZ * sizeof(double)));
-    CK(cudaMalloc(&d_coef, 6 * nodes * sizeof(double)));
-    CK(cudaMalloc(&d_c1, 2 * (size_t)(n_prof + 2) * sizeof(double)));
+    dev_ptr<double> o_raw, o_tmp, o_coef, o_c1, o_cpR, o_cpZ;
+    CK(dev_alloc(o_raw, 6 * npts));
+    CK(dev_alloc(o_tmp, (size_t)sr * nZ));
+    CK(dev_alloc(o_coef, 6 * nodes));
+    CK(dev_alloc(o_c1, 2 * (size_t)(n_prof + 2)));
     std::vector<double> cpR = thomas_pivots(nR), cpZ = thomas_pivots(nZ);
-    CK(cudaMalloc(&d_cpR, cpR.size() * sizeof(double)));
-    CK(cudaMalloc(&d_cpZ, cpZ.size() * sizeof(double)));
+    CK(dev_alloc(o_cpR, cpR.size()));
+    CK(dev_alloc(o_cpZ, cpZ.size()));
+    double *d_raw = o_raw.get(), *d_tmp = o_tmp.get(), *d_coef = o_coef.get(), *d_c1 = o_c1.get(), *d_cpR = o_cpR.get(),
+           *d_cpZ = o_cpZ.get();
     const double* src[6] = {psi_norm, nullptr, nullptr, BR, BZ, Bphi};  // field order: psi, lnne, lnTe, BR, BZ, Bphi
     for (int f = 0; f < 6; ++f)
         if (src[f]) CK(cudaMemcpyAsync(d_raw + f * npts, src[f], npts * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -392,6 +423,7 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
     }
     CK(cudaGetLastError());
     torj_plasma* p = new torj_plasma();
+    Guard<torj_plasma, torj_plasma_destroy> guard(p);
     p->ctx = c;
     p->id = ++g_plasma_serial;
     CK(cudaMalloc(&p->dA, 2 * nodes * sizeof(double2)));
@@ -401,7 +433,6 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_raw); cudaFree(d_tmp); cudaFree(d_coef); cudaFree(d_c1); cudaFree(d_cpR); cudaFree(d_cpZ);
     DevTables& T = p->T;
     T.A = p->dA; T.B = p->dB;
     T.nR = nR; T.nZ = nZ; T.row = sr;
@@ -414,7 +445,7 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
     CK(cudaMemcpy(p->dT, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
     p->vol_c = vc;
     p->n_vol = n_1d; p->vol_x0 = vr[0]; p->vol_h = (vr[n_1d - 1] - vr[0]) / (double)(n_1d - 1);
-    *out = p;
+    *out = guard.release();
     return 0;
 }
 
@@ -462,10 +493,11 @@ int torj_probe(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
     if (!c->gl_set) FAIL("The weights and abscissae for the absorption were never initialized. Call `abs_Al_init` before using the absorption.");
     if (set_device(c)) return 1;
     SolverOpts so = to_sopts(opt, 1.0);
-    double *dx, *dN, *dout;
-    CK(cudaMalloc(&dx, 3 * n * sizeof(double)));
-    CK(cudaMalloc(&dN, 3 * n * sizeof(double)));
-    CK(cudaMalloc(&dout, 11 * n * sizeof(double)));
+    dev_ptr<double> o_x, o_N, o_out;
+    CK(dev_alloc(o_x, 3 * (size_t)n));
+    CK(dev_alloc(o_N, 3 * (size_t)n));
+    CK(dev_alloc(o_out, 11 * (size_t)n));
+    double *dx = o_x.get(), *dN = o_N.get(), *dout = o_out.get();
     CK(cudaMemcpyAsync(dx, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dN, N, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     k_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, dout);
@@ -473,7 +505,6 @@ int torj_probe(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout, 11 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dx); cudaFree(dN); cudaFree(dout);
     return 0;
 }
 
@@ -482,16 +513,16 @@ int torj_rhs(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t
     if (!c->gl_set) FAIL("The weights and abscissae for the absorption were never initialized. Call `abs_Al_init` before using the absorption.");
     if (set_device(c)) return 1;
     SolverOpts so = to_sopts(opt, 1.0);
-    double *d_u, *d_du;
-    CK(cudaMalloc(&d_u, 7 * n * sizeof(double)));
-    CK(cudaMalloc(&d_du, 7 * n * sizeof(double)));
+    dev_ptr<double> o_u, o_du;
+    CK(dev_alloc(o_u, 7 * (size_t)n));
+    CK(dev_alloc(o_du, 7 * (size_t)n));
+    double *d_u = o_u.get(), *d_du = o_du.get();
     CK(cudaMemcpyAsync(d_u, u, 7 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     k_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, d_du);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(du, d_du, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_u); cudaFree(d_du);
     return 0;
 }
 
@@ -521,6 +552,7 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     if (!c || !out || n < 1) FAIL("torj_bundle_create: bad argument");
     if (set_device(c)) return 1;
     torj_bundle* b = new torj_bundle();
+    Guard<torj_bundle, torj_bundle_destroy> guard(b);
     b->ctx = c; b->n = n; b->per_ray_fm = per_ray_fm;
     size_t nf = per_ray_fm ? (size_t)n : 1;
     CK(cudaMalloc(&b->d_pos, 3 * n * sizeof(double)));
@@ -542,7 +574,7 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     B.per_ray_fm = per_ray_fm; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
     B.P_final = b->d_Pf; B.P_dep = b->d_Pdep; B.n_points = b->d_npts;
     if (bundle_upload(b, pos, dir, weight, freq_hz, mode)) return 1;
-    *out = b;
+    *out = guard.release();
     return 0;
 }
 
@@ -577,6 +609,7 @@ int torj_bundle_create_from_launchers(torj_ctx* c, int32_t n_launchers, const do
     // an empty bundle shell with device arrays, then the generator kernel fills pos/dir/weight/freq/mode/beam
     std::vector<double> zero3(3, 0.0);
     torj_bundle* b = new torj_bundle();
+    Guard<torj_bundle, torj_bundle_destroy> guard(b);
     b->ctx = c; b->n = n; b->per_ray_fm = 1;
     CK(cudaMalloc(&b->d_pos, 3 * n * sizeof(double)));
     CK(cudaMalloc(&b->d_dir, 3 * n * sizeof(double)));
@@ -600,9 +633,10 @@ int torj_bundle_create_from_launchers(torj_ctx* c, int32_t n_launchers, const do
     B.P_final = b->d_Pf; B.P_dep = b->d_Pdep; B.n_points = b->d_npts;
     // launcher parameters to the device
     const size_t nl = n_launchers;
-    double* d_par = nullptr; int* d_ipar = nullptr;
-    CK(cudaMalloc(&d_par, (9 * nl + 2 * N_rings) * sizeof(double)));
-    CK(cudaMalloc(&d_ipar, (nl + N_rings + 1) * sizeof(int)));
+    dev_ptr<double> o_par; dev_ptr<int> o_ipar;
+    CK(dev_alloc(o_par, 9 * nl + 2 * N_rings));
+    CK(dev_alloc(o_ipar, nl + N_rings + 1));
+    double* d_par = o_par.get(); int* d_ipar = o_ipar.get();
     cudaStream_t st = c->stream;
     CK(cudaMemcpyAsync(d_par, x0, 3 * nl * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_par + 3 * nl, N0, 3 * nl * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -624,8 +658,7 @@ int torj_bundle_create_from_launchers(torj_ctx* c, int32_t n_launchers, const do
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_par); cudaFree(d_ipar);
-    *out = b;
+    *out = guard.release();
     if (n_rays_out) *n_rays_out = n;
     return 0;
 }
@@ -709,6 +742,8 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (b->n_psi != n_psi || b->prof_rows != b->n_beams) {
         CK(cudaStreamSynchronize(st));
         cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV); cudaFree(b->d_profile);
+        b->d_edges = b->d_bins = b->d_dV = b->d_profile = nullptr;  // a failing allocation below must not leave them dangling
+        b->n_psi = 0; b->prof_rows = 0;
         b->h_edges.clear();
         CK(cudaMalloc(&b->d_edges, n_psi * sizeof(double)));
         CK(cudaMalloc(&b->d_bins, (size_t)b->n_beams * (n_psi + 2) * sizeof(double)));
@@ -720,6 +755,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (b->traj_count > 0 && b->traj_prof_npsi != n_psi) {
         CK(cudaStreamSynchronize(st));
         cudaFree(b->d_tprof);
+        b->d_tprof = nullptr; b->traj_prof_npsi = 0;
         CK(cudaMalloc(&b->d_tprof, (size_t)b->traj_count * n_psi * sizeof(double)));
         b->traj_prof_npsi = n_psi;
     }
@@ -771,18 +807,15 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     // absorption coefficient on every trip (measured 3.1 s -> 2.4 s). Below one wave there is nothing to balance.
     const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB;
     int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes);
-    if (od.n_segments < 2) interleave = 0;
+    if (od.n_segments < 2 || b->n > 0x7fffffff) interleave = 0;
     a.interleave = interleave; a.hand = nullptr; a.seg_done = nullptr; a.rays_left = nullptr;
     if (interleave) {
-        if (!b->d_hand) {
-            CK(cudaMalloc(&b->d_hand, (size_t)b->n * TORJ_HAND_D * sizeof(double)));
-            CK(cudaMalloc(&b->d_segdone, (size_t)b->n * sizeof(int)));
-            CK(cudaMalloc(&b->d_left, sizeof(int)));
-        }
-        const int left = (int)b->n;
+        if (!b->d_hand) CK(cudaMalloc(&b->d_hand, (size_t)b->n * TORJ_HAND_D * sizeof(double)));
+        if (!b->d_segdone) CK(cudaMalloc(&b->d_segdone, (size_t)b->n * sizeof(int)));
+        if (!b->d_left) CK(cudaMalloc(&b->d_left, sizeof(int)));
+        b->h_left = (int)b->n;
         CK(cudaMemsetAsync(b->d_segdone, 0, (size_t)b->n * sizeof(int), st));
-        CK(cudaMemcpyAsync(b->d_left, &left, sizeof left, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));  // `left` is a local
+        CK(cudaMemcpyAsync(b->d_left, &b->h_left, sizeof(int), cudaMemcpyHostToDevice, st));
         a.hand = b->d_hand; a.seg_done = b->d_segdone; a.rays_left = b->d_left;
     }
     CK(cudaEventRecord(c->ev0, st));
@@ -1017,11 +1050,16 @@ int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* 
 
 int torj_fp64_peak(torj_ctx* c, int32_t iters, double* tflops, double* ms) {
     if (set_device(c)) return 1;
-    double* d;
-    CK(cudaMalloc(&d, sizeof(double)));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    dev_ptr<double> o_d;
+    CK(dev_alloc(o_d, 1));
+    double* d = o_d.get();
+    struct Ev {
+        cudaEvent_t e = nullptr;
+        ~Ev() { if (e) cudaEventDestroy(e); }
+    } ev0, ev1;
+    CK(cudaEventCreate(&ev0.e));
+    CK(cudaEventCreate(&ev1.e));
+    cudaEvent_t e0 = ev0.e, e1 = ev1.e;
     int blocks = c->num_sms * 8, threads = 256;
     k_dfma<<<blocks, threads, 0, c->stream>>>(iters / 8 + 1, d);  // warm-up
     c->launches++;
@@ -1035,23 +1073,22 @@ int torj_fp64_peak(torj_ctx* c, int32_t iters, double* tflops, double* ms) {
     double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
     if (ms) *ms = t;
     if (tflops) *tflops = flops / (t * 1e-3) / 1e12;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return 0;
 }
 
 // cycles per dependent DFMA (single warp, single chain)
 int torj_fp64_latency(torj_ctx* c, int32_t iters, double* cycles_per_dfma) {
     if (set_device(c)) return 1;
-    double* d; long long* dc;
-    CK(cudaMalloc(&d, sizeof(double)));
-    CK(cudaMalloc(&dc, sizeof(long long)));
+    dev_ptr<double> o_d; dev_ptr<long long> o_dc;
+    CK(dev_alloc(o_d, 1));
+    CK(dev_alloc(o_dc, 1));
+    double* d = o_d.get(); long long* dc = o_dc.get();
     k_dfma_latency<<<1, 32, 0, c->stream>>>(iters, 1.0, d, dc);
     c->launches++;
     long long cyc = 0;
     CK(cudaMemcpyAsync(&cyc, dc, sizeof cyc, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     *cycles_per_dfma = (double)cyc / (16.0 * (double)iters);
-    cudaFree(d); cudaFree(dc);
     return 0;
 }
 
@@ -1059,16 +1096,16 @@ int torj_fp64_latency(torj_ctx* c, int32_t iters, double* cycles_per_dfma) {
 int torj_math_probe(torj_ctx* c, int64_t n, const double* x, double* out) {
     if (!c || n < 1 || !x || !out) FAIL("torj_math_probe: bad argument");
     if (set_device(c)) return 1;
-    double *dx, *dout;
-    CK(cudaMalloc(&dx, n * sizeof(double)));
-    CK(cudaMalloc(&dout, 4 * n * sizeof(double)));
+    dev_ptr<double> o_x, o_out;
+    CK(dev_alloc(o_x, (size_t)n));
+    CK(dev_alloc(o_out, 4 * (size_t)n));
+    double *dx = o_x.get(), *dout = o_out.get();
     CK(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     k_math_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, dx, dout);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dx); cudaFree(dout);
     return 0;
 }
 
