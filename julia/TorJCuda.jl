@@ -21,6 +21,7 @@ torj_check(rc) = rc == 0 || error(unsafe_string(ccall((:torj_last_error, libtorj
 const _ctx = Ref{Ptr{Cvoid}}(C_NULL)
 function torj_ctx()
     if _ctx[] == C_NULL
+        @assert ccall((:torj_abi_version, libtorj), Cint, ()) == 2   # the struct layouts above are TORJ_ABI_VERSION 2
         torj_check(ccall((:torj_ctx_create, libtorj), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), 0, C_NULL, _ctx))
     end
     _ctx[]
