@@ -604,13 +604,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             }
             act = ACT_BEGIN_STEP;
         } else if (phase == PH_STAGE) {
-            {
-                const double bj = s_bt[st];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    KK(st, i) = out[i];
-                }
-            }
+            for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
             if (st < S - 1) {
                 st++;
                 // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
@@ -710,7 +705,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 dt = fmin(dt, tstop - t);
                 st = 1;
                 {
-                    const double a10 = dt * s_a[1][0], b0 = s_bt[0];
+                    const double a10 = dt * s_a[1][0];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
                         const double k0 = KK(0, i);
