@@ -470,7 +470,9 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M
 // x_m <= 3.2 (m=2 layer: x_m ~ 1; m=3 next to it: x_m ~ 2); K=24 for x_m <= 6.5; libm jn() beyond.
 // One sqrt per harmonic; everything else is products of the reciprocals prepared in abs_albajar.
 // `safe` is cleared unless the bound is below floor * TORJ_SKIP_MARGIN (see abs_albajar).
+#ifndef TORJ_SKIP_MARGIN
 #define TORJ_SKIP_MARGIN 1e-10
+#endif
 // M = 0: order given at run time (harmonics above the reference's third; libm jn() throughout).
 template <int M>
 __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe, int m_rt = M) {
