@@ -141,3 +141,22 @@ def test_block_cyclic_sharding_partitions_the_rays():
         assert all(np.all(np.diff(p) > 0) for p in parts if len(p) > 1)
     p = shard_block_cyclic(1049600, 1025, 3, 8)
     assert p[0] == 3 * 1025 and p[1025] == 11 * 1025 and len(p) == 128 * 1025
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the package, its CUDA sources or the built library may import, include
+    or link it, and importing the package must not load it."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "torj_jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                pat = (r"^\s*(from|import)\s+[^#\n]*oracle|ctypes[^\n]*oracle|CDLL[^\n]*oracle" if f.endswith(".py")
+                       else r"^\s*#\s*include[^\n]*oracle" if not f.endswith("Makefile") else r"^[^#\n]*oracle")
+                assert not re.search(pat, txt, flags=re.M | re.I), f"{os.path.join(dirpath, f)} uses the oracle"
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    code = "import sys; sys.path.insert(0, %r); import torj_jl_b200; print(any('oracle' in m for m in sys.modules))" % ROOT
+    assert subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout.strip() == "False"
