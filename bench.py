@@ -104,6 +104,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def cpu_model():
+    """`model name` of /proc/cpuinfo (the CPU baseline names the host it ran on)."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(rank_bundle, seconds_target=15.0):
     """Oracle port on all host cores over a bounded sample of the same bundle (rays spread evenly over it)."""
     import torj_jl_b200 as tj
@@ -126,7 +138,7 @@ def cpu_baseline(rank_bundle, seconds_target=15.0):
                      deposition="streaming", n_threads=cores)
     dt_s = (time.perf_counter() - t1) * 4.0  # quarter sample, scaled: the GPU's deposition algorithm on the CPU
     return dict(value=r["counters"]["n_acc"] / dt, value_streaming_deposition=r["counters"]["n_acc"] / dt_s,
-                unit="ray-steps/s", cores=cores, kind="port",
+                unit="ray-steps/s", cores=cores, kind="port", cpu=cpu_model(),
                 sample=f"{n_sample} of {len(w)} rays of the same bundle, evenly spaced, reference deposition algorithm, {dt:.1f} s",
                 rays_per_s=n_sample / dt, seconds=dt, n_rays=n_sample, steps=int(r["counters"]["n_acc"]))
 
@@ -149,7 +161,8 @@ def run_reference_arm(args):
             "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD["name"], **{k: WORKLOAD[k] for k in ("n_rays", "grid", "s_max", "n_psi", "f", "mode")},
                        "note": "Julia reference not runnable here (no Julia); CPU oracle port, OpenMP over rays"},
-            "cpu_baseline": {"value": v, "unit": "ray-steps/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "cpu_baseline": {"value": v, "unit": "ray-steps/s", "cores": last["cores"], "cpu": last["cpu"], "kind": "port",
+                             "sample": last["sample"]},
             "rays_per_s": float(np.mean([x["rays_per_s"] for x in vals])),
             "e2e": {"value": v, "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -302,7 +315,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                 "absorbed_fraction": dep.value / max(1, world) if world > 1 else dep.value}
         if not args.no_cpu_baseline and world >= 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline((pos, dirs, w)).items() if k in ("value", "value_streaming_deposition", "unit", "cores", "kind", "sample", "rays_per_s")}
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline((pos, dirs, w)).items() if k in ("value", "value_streaming_deposition", "unit", "cores", "cpu", "kind", "sample", "rays_per_s")}
         print(json.dumps(line), flush=True)
     L.torj_bundle_destroy(bh)
     if world > 1:
