@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TORJ_ABI_VERSION 2
+#define TORJ_ABI_VERSION 3
 
 typedef struct torj_ctx torj_ctx;       /* one per (process, device): stream, quadrature nodes, launch counter */
 typedef struct torj_plasma torj_plasma; /* device-resident equilibrium tables (reference struct Plasma, src/plasma.jl:2-14) */
@@ -36,7 +36,9 @@ enum {
     TORJ_RAY_OK = 0,
     TORJ_RAY_CUTOFF_AT_ENTRY = 1, /* reference src/solve.jl:55-59 returns (false, nothing) */
     TORJ_RAY_INIT_FAILED = 2,     /* bisection bracket (src/solve.jl:29), asserts src/solve.jl:32,138,141, Newton failure */
-    TORJ_RAY_LEFT_GRID = 3,
+    TORJ_RAY_LEFT_GRID = 3,       /* informational, like 6: the ray ended outside the (R,Z) grid box, where every field is the
+                                     splines' linear extrapolation (Interpolations.jl `Line()`, src/plasma.jl:36-41); it was
+                                     traced and deposited to the end exactly as the reference does */
     TORJ_RAY_MAX_STEPS = 4,
     TORJ_RAY_NAN = 5,
     TORJ_RAY_TRAJ_TRUNCATED = 6   /* trajectory window full; tracing and deposition still completed */
@@ -67,6 +69,17 @@ typedef struct torj_options {
                                       segments, so all rays advance together: no partly filled last wave, and the lanes
                                       of a warp stay in step (automatic picks this when the bundle exceeds the resident
                                       lanes, 37 888 on a B200) */
+    int32_t absorption_model;      /* 0 = Albajar (reference src/absorption.jl:191-235, what the reference's gradΛ! calls);
+                                      1 = warm-plasma damping: alpha = α(ω, X, Y, |N|, acos(N∥/|N|), Te, v_g_perp, mode)[2] of
+                                      reference src/general_absorption.jl:1328-1337 (iwarm = 3, Larmor order lrm <= 5) in the
+                                      place of α_approx. That file is dead code in the reference (never include()d), so the
+                                      wiring is BUILD-DEFINED: v_g_perp = 1/|dΛ/dN|, same Te gate
+                                      (te_min); the debug assertion at :314-316 is dropped (it calls an un-imported function).
+                                      With alpha_floor > 0 the 501-node quadrature is skipped where the anti-Hermitian part is
+                                      below the floor by construction (torj_warm.cuh); 0 evaluates it everywhere */
+    int32_t lanes_per_ray;         /* 0 = automatic; 1 = one GPU thread per ray; 32 = a warp per ray (the nodes of the harmonic
+                                      integrals / of the warm quadrature are split over the lanes): for bundles far below the
+                                      resident lanes and for the warm model. Results agree to rounding (summation order) */
     int32_t reserved_;             /* keeps the struct size a multiple of 8; must be 0 */
 } torj_options;
 
@@ -74,8 +87,9 @@ typedef struct torj_counters {
     int64_t n_acc;   /* accepted integrator steps (the "ray-steps" of the headline metric) */
     int64_t n_rej;   /* rejected steps */
     int64_t n_rhs;   /* evaluations of gradΛ! (src/solve.jl:85-95) */
-    int64_t n_alpha; /* abs_Albajar_fast calls past the Te gate (src/absorption.jl:194) */
-    int64_t n_harm;  /* harmonic integrals evaluated (src/absorption.jl:217) */
+    int64_t n_alpha; /* abs_Albajar_fast calls past the Te gate (src/absorption.jl:194); warm model: α calls past the gate */
+    int64_t n_harm;  /* harmonic integrals evaluated (src/absorption.jl:217); warm model: resonance indices n integrated over
+                        the 501 nodes (2 llm + 1 per α call, src/general_absorption.jl:669-710) */
     int64_t n_rays_ok;
     int64_t n_harm_pruned; /* harmonic integrals skipped by the alpha_floor bound */
     int64_t n_alpha_skipped; /* inner Runge-Kutta stages that took alpha = 0 on the 1e10-margin rule (alpha_floor > 0 only) */
@@ -101,8 +115,18 @@ int64_t torj_ctx_launch_count(const torj_ctx* ctx);
 /* device duration (CUDA events on the context stream) of the most recent trace-kernel launch; synchronises on it */
 int torj_ctx_last_trace_ms(torj_ctx* ctx, double* ms);
 
-/* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64). */
+/* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64).
+ * Like the reference's module globals (src/constants.jl:7-8) the table is shared: ONE per device. A context created on
+ * a device whose table is already set inherits it; setting different nodes synchronises the whole device first and
+ * changes them for every context on that device. */
 int torj_abs_init(torj_ctx* ctx, int32_t n, const double* nodes, const double* weights);
+
+/* α(omega, X, Y, N_r, theta, te, v_g_perp, imod) — reference src/general_absorption.jl:1328-1337, at n points (arrays
+ * of length n): N_warm = Re(N_perp)/sin(theta) and alpha = 2 Im(N_perp^2) omega/c v_g_perp; lrm = min(5, larmornumber),
+ * ierr = 99 (negative solution, :1229-1232) / 98 (lrm < 1: the reference throws). set_extv! (:8-13) needs no call. */
+int torj_warm_alpha(torj_ctx* ctx, int64_t n, const double* omega, const double* X, const double* Y, const double* N_r,
+                    const double* theta, const double* te, const double* v_g_perp, int32_t imod, double* N_warm,
+                    double* alpha, int32_t* lrm, int32_t* ierr);
 
 /* --- equilibrium ------------------------------------------------------------------------------------------- */
 /* Host helper: cubic B-spline prefilter of cubic_spline_interpolation((r,z), data) — reference src/plasma.jl:36-41
@@ -165,12 +189,21 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
 /* Device pointer to n_beams x (n_psi+2) doubles: dP_dV[n_psi], deposited_power, sum of weights per beam — for a caller-side
  * NCCL all-reduce (sum) across GPUs; valid after torj_bundle_trace, ordered on the context stream. */
 void* torj_bundle_device_profile(torj_bundle* b);
-/* Synchronises and copies results to the host (any pointer may be NULL). */
+/* Synchronises and copies results to the host (any pointer may be NULL). For a ray that failed initialisation
+ * (status 1 or 2) P_final and P_deposited_ray are 0 and n_points is minus the failing check's number (-1 no grid entry,
+ * -2 no psi bracket, -3/-4 asserts of src/solve.jl:32,138, -5..-7 Newton, -8 assert :141, -9 cut-off :55-59). */
 int torj_bundle_results(torj_bundle* b, double* dP_dV, double* deposited_power, double* P_final,
                         double* P_deposited_ray, int32_t* n_points, int32_t* status, torj_counters* counters);
 /* Trajectory window to the host: arrays [traj_count][traj_max_pts] (s, P, dP_ds), [traj_count][3][traj_max_pts]
  * (xyz) and the per-ray profile [traj_count][n_psi]; any pointer may be NULL. */
 int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, double* dP_ds, double* dP_dV_ray);
+/* Derived ray coordinates (the reference integrates Cartesian u = [x, N, P], src/solve.jl:144; these are the cylindrical
+ * position and the optical depth of the same state): R = hypot(x, y), phi = atan2(y, x), tau = -ln P.
+ * torj_bundle_final_state: state at retirement of every ray, u_final [7][n] and/or R, phi, tau [n]; rays that failed
+ * initialisation get NaN. torj_bundle_trajectories_cyl: the same per sample of the trajectory window,
+ * [traj_count][traj_max_pts] each. Any pointer may be NULL. */
+int torj_bundle_final_state(torj_bundle* b, double* u_final, double* R, double* phi, double* tau);
+int torj_bundle_trajectories_cyl(torj_bundle* b, double* R, double* phi, double* tau);
 
 /* --- one-shot host-buffer call: what the Julia make_ray / make_beam shims ccall ------------------------------ */
 int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
@@ -183,14 +216,21 @@ int torj_trace(torj_ctx* ctx, const torj_plasma* p, const torj_options* opt, int
 
 /* --- single-process multi-GPU front end ----------------------------------------------------------------------- */
 /* For a host that is ONE process on a multi-GPU box (a Julia session calling make_beam): the same call as torj_trace,
- * sharded by contiguous ray blocks over the devices (one host thread and one context per device, tables replicated),
- * with the weighted sum of reference src/solve.jl:233-240 done on the host in device order — bit-reproducible for a
- * given device count. (bench.py uses one process per GPU and an NCCL all-reduce instead.) */
+ * sharded over the devices (one persistent worker thread, one context and pinned staging buffers per device, tables
+ * replicated). The weighted sum of reference src/solve.jl:233-240 across devices is ONE ncclAllReduce(sum, double,
+ * n_beams * (n_psi + 2)) over NVLink on the devices' profile buffers (communicators from ncclCommInitAll at
+ * torj_multi_create; libnccl.so.2 is loaded at run time), or — reduction = 1, and whenever NCCL is unavailable — a
+ * host sum in device order, bit-reproducible for a given device count.
+ * sharding: 0 = contiguous ray blocks; 1 = block-cyclic, blocks of `block_rays` consecutive rays (one beam) dealt
+ * round-robin, which balances scans whose beams differ in ray length. */
 typedef struct torj_multi torj_multi;
 typedef struct torj_mplasma torj_mplasma;
 int torj_multi_create(int32_t n_devices /* <= 0: all visible */, torj_multi** out);
 void torj_multi_destroy(torj_multi* m);
 int32_t torj_multi_device_count(const torj_multi* m);
+int torj_multi_configure(torj_multi* m, int32_t sharding, int64_t block_rays, int32_t reduction);
+/* 1 when the cross-device sum of the last torj_multi_trace went through ncclAllReduce, 0 for the host sum */
+int32_t torj_multi_used_nccl(const torj_multi* m);
 int torj_multi_abs_init(torj_multi* m, int32_t n, const double* nodes, const double* weights);
 int torj_multi_plasma_create_from_data(torj_multi* m, const torj_grid* grid, const double* psi_norm, const double* psi_prof,
                                        const double* ne_prof, const double* Te_prof, int32_t n_prof, const double* BR,

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <complex>
 #include <vector>
+#include "general_absorption.hpp"
 #include "plasma.hpp"
 
 namespace torj_oracle {
@@ -133,6 +134,7 @@ struct RayParams {
     int mode;
     double te_min = 20.0;   // reference src/absorption.jl:194
     int max_harmonic = 3;   // reference src/absorption.jl:199
+    int absorption_model = 0;  // 0 = Albajar (src/absorption.jl), 1 = warm-plasma α (src/general_absorption.jl:1328-1337)
 };
 
 // reference src/absorption.jl:228-235
@@ -142,6 +144,23 @@ inline double alpha_approx(const Plasma& pl, const AbsQuad& q, const RayParams& 
     PlasmaPoint<double> p = eval_plasma<double>(pl, x, N, rp.omega);
     double Te = std::exp(evaluate<double>(pl.lnTe, x));
     return abs_Albajar_fast(q, rp.omega, p.X, p.Y, N_abs, p.N_par, Te, rp.mode, rp.te_min, rp.max_harmonic, cnt);
+}
+
+// Warm-plasma damping in the place of α_approx. The reference never wires general_absorption.jl's α into gradΛ!
+// (the file is not even include()d), so this wiring is BUILD-DEFINED (SURVEY.md §8(a) a21 "proposed wiring"):
+//   α_warm = α(ω, X, Y, |N|, acos(N∥/|N|), Te, v_g_perp = 1/|∂Λ/∂N|, mode)[2]
+// with the same Te gate as abs_Albajar_fast (src/absorption.jl:194). n_harm counts the (2 llm + 1) resonance indices n
+// of the Hermitian quadrature (src/general_absorption.jl:669-710), i.e. 501 expei evaluations each.
+inline double alpha_warm_approx(const Plasma& pl, const RayParams& rp, const double x[3], const double N[3],
+                                double v_g_perp, AbsCounters* cnt) {
+    double N_abs = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+    PlasmaPoint<double> p = eval_plasma<double>(pl, x, N, rp.omega);
+    double Te = std::exp(evaluate<double>(pl.lnTe, x));
+    if (Te < rp.te_min) return 0.0;
+    double theta = std::acos(p.N_par / N_abs);
+    warm::AlphaOut o = warm::alpha(rp.omega, p.X, p.Y, N_abs, theta, Te, v_g_perp, rp.mode);
+    if (cnt) { cnt->n_alpha++; cnt->n_harm += 2 * std::min(3, o.lrm) + 1; }
+    return o.alpha;
 }
 
 }  // namespace torj_oracle

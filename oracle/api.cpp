@@ -25,6 +25,9 @@ struct oracle_options {  // the reference's hard-coded solver constants (the ora
     double dtmax, abstol, reltol, psi_stop, p_stop, te_min;
     int32_t max_harmonic;
     int32_t max_steps_per_segment;
+    int32_t absorption_model;  // 0 Albajar, 1 warm-plasma α (general_absorption.jl)
+    int32_t reserved_;
+    double alpha_floor;        // > 0: the CUDA path's two work-saving rules, for a like-for-like CPU timing
 };
 
 static Options to_opts(const oracle_options* o) {
@@ -33,6 +36,8 @@ static Options to_opts(const oracle_options* o) {
     r.scheme = o->scheme; r.n_segments = o->n_segments; r.dtmax = o->dtmax; r.abstol = o->abstol; r.reltol = o->reltol;
     r.psi_stop = o->psi_stop; r.p_stop = o->p_stop; r.te_min = o->te_min; r.max_harmonic = o->max_harmonic;
     r.max_steps_per_segment = o->max_steps_per_segment;
+    r.absorption_model = o->absorption_model;
+    r.alpha_floor = o->alpha_floor;
     return r;
 }
 
@@ -91,12 +96,59 @@ void oracle_rhs(void* h, const double* gl_t, const double* gl_w, int n_gl, const
     RayParams rp; rp.omega = 2.0 * M_PI * f; rp.mode = mode; rp.te_min = te_min; rp.max_harmonic = max_harmonic;
     grad_lambda(*(Plasma*)h, q, rp, u, du, nullptr);
 }
+void oracle_rhs_model(void* h, const double* gl_t, const double* gl_w, int n_gl, const double* u, double f, int mode,
+                      double te_min, int max_harmonic, int absorption_model, double* du) {
+    AbsQuad q; q.t.assign(gl_t, gl_t + n_gl); q.w.assign(gl_w, gl_w + n_gl);
+    RayParams rp; rp.omega = 2.0 * M_PI * f; rp.mode = mode; rp.te_min = te_min; rp.max_harmonic = max_harmonic;
+    rp.absorption_model = absorption_model;
+    grad_lambda(*(Plasma*)h, q, rp, u, du, nullptr);
+}
 double oracle_abs_albajar(const double* gl_t, const double* gl_w, int n_gl, double omega, double X, double Y,
                           double N_abs, double N_par, double Te, int mode, double te_min, int max_harmonic) {
     AbsQuad q; q.t.assign(gl_t, gl_t + n_gl); q.w.assign(gl_w, gl_w + n_gl);
     return abs_Albajar_fast(q, omega, X, Y, N_abs, N_par, Te, mode, te_min, max_harmonic, nullptr);
 }
 double oracle_besselj(int n, double x) { return jn(n, x); }
+
+// ---- warm-plasma absorption (reference src/general_absorption.jl), exposed piece by piece for pinning ----
+double oracle_expei(double x) { return warm::expei(x); }
+double oracle_gammln(double x) { return warm::gammln(x); }
+double oracle_fact(int k) { return warm::fact(k); }
+// out[l+2]: orders n..l+2
+int oracle_ssbi(double zz, int n, int l, double* out) {
+    std::vector<double> v = warm::ssbi(zz, n, l);
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return (int)v.size();
+}
+void oracle_zetac(double xi, double yi, double* re_im) {
+    warm::cplx z = warm::zetac(xi, yi);
+    re_im[0] = z.real(); re_im[1] = z.imag();
+}
+int oracle_larmornumber(double yg, double npl, double mu) { return warm::larmornumber(yg, npl, mu); }
+// rr[(2 lrm + 1)][3][lrm + 1] (n = -lrm..lrm, k, m), row-major
+void oracle_hermitian(double yg, double anpl, double amu, int lrm, int iwarm, double* rr) {
+    warm::RR r = warm::hermitian(yg, anpl, amu, lrm, iwarm);
+    std::memcpy(rr, r.v.data(), r.v.size() * sizeof(double));
+}
+// ri[lrm][3][lrm] (n = 1..lrm, k, m = 1..lrm), row-major
+void oracle_antihermitian(double yg, double anpl, double amu, int lrm, double* ri) {
+    warm::RI r = warm::antihermitian(yg, anpl, amu, lrm);
+    std::memcpy(ri, r.v.data(), r.v.size() * sizeof(double));
+}
+// out[10]: Re/Im of N_perp, ex, ey, ez, then ierr, iterations
+void oracle_warmdisp(double xg, double yg, double anpl, double amu, double anprc, int sox, int iwarm, int lrm, double* out) {
+    warm::WarmDisp w = warm::warmdisp(xg, yg, anpl, amu, anprc, sox, iwarm, lrm);
+    out[0] = w.anpr.real(); out[1] = w.anpr.imag(); out[2] = w.ex.real(); out[3] = w.ex.imag(); out[4] = w.ey.real();
+    out[5] = w.ey.imag(); out[6] = w.ez.real(); out[7] = w.ez.imag(); out[8] = w.ierr; out[9] = w.iterations;
+}
+// α(omega, X, Y, N_r, theta, te, v_g_perp, imod) of reference src/general_absorption.jl:1328-1337.
+// out[7]: N_warm, alpha, lrm, ierr, iterations, Re N_perp, Im N_perp
+void oracle_warm_alpha(double omega, double X, double Y, double N_r, double theta, double te, double v_g_perp, int imod,
+                       double* out) {
+    warm::AlphaOut o = warm::alpha(omega, X, Y, N_r, theta, te, v_g_perp, imod);
+    out[0] = o.N_warm; out[1] = o.alpha; out[2] = o.lrm; out[3] = o.ierr; out[4] = o.iterations;
+    out[5] = o.N_perp.real(); out[6] = o.N_perp.imag();
+}
 
 void oracle_gausshermite(int n, double* x, double* w) {
     std::vector<double> xv, wv;

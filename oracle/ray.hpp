@@ -43,6 +43,10 @@ struct Options {
     double te_min = 20.0;      // reference src/absorption.jl:194
     int max_harmonic = 3;      // reference src/absorption.jl:199
     int max_steps_per_segment = 100000;
+    int absorption_model = 0;  // 0 = Albajar, 1 = warm-plasma α of src/general_absorption.jl (wiring build-defined)
+    // The two work-saving rules of the CUDA path (include/torj_cuda.h: alpha_floor), restated so that the CPU arm of
+    // bench.py can be timed doing the same work; 0 = evaluate everything as the reference does.
+    double alpha_floor = 0.0;
 };
 
 struct RayCounters {
@@ -76,7 +80,8 @@ inline void grad_lambda(const Plasma& pl, const AbsQuad& q, const RayParams& rp,
         du[k] = LN.d[k] / nrm;
         du[3 + k] = -(Lx.d[k] / nrm);
     }
-    du[6] = -u[6] * alpha_approx(pl, q, rp, u, u + 3, cnt ? &cnt->abs : nullptr);
+    if (rp.absorption_model == 1) du[6] = -u[6] * alpha_warm_approx(pl, rp, u, u + 3, 1.0 / nrm, cnt ? &cnt->abs : nullptr);
+    else du[6] = -u[6] * alpha_approx(pl, q, rp, u, u + 3, cnt ? &cnt->abs : nullptr);
     if (cnt) cnt->n_rhs++;
 }
 
@@ -318,6 +323,7 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
     rp.mode = mode;
     rp.te_min = opt.te_min;
     rp.max_harmonic = opt.max_harmonic;
+    rp.absorption_model = opt.absorption_model;
     const Tableau& tb = opt.scheme == 1 ? tableau_owrenzen3() : tableau_tsit5();
     const int S = tb.stages;
 
@@ -422,6 +428,8 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
             if (EEst <= 1.0) {
                 res.cnt.n_acc++;
                 qold = std::max(EEst, qoldinit);
+                // OrdinaryDiffEq step_accept_controller! (PIController): q := 1 inside [qsteady_min, qsteady_max] = [1, 1.2]
+                if (qq >= 1.0 && qq <= 1.2) qq = 1.0;
                 double dtnew = dt / qq;
                 double ttmp = t + dt;
                 if (std::fabs(ttmp - tstop) < 100.0 * eps_of(std::max(t, tstop))) ttmp = tstop;

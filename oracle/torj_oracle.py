@@ -21,11 +21,12 @@ c_ip = C.POINTER(C.c_int32)
 class OracleOptions(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("n_segments", C.c_int32), ("dtmax", C.c_double), ("abstol", C.c_double),
                 ("reltol", C.c_double), ("psi_stop", C.c_double), ("p_stop", C.c_double), ("te_min", C.c_double),
-                ("max_harmonic", C.c_int32), ("max_steps_per_segment", C.c_int32)]
+                ("max_harmonic", C.c_int32), ("max_steps_per_segment", C.c_int32), ("absorption_model", C.c_int32),
+                ("reserved_", C.c_int32), ("alpha_floor", C.c_double)]
 
     @classmethod
     def default(cls, **kw):
-        o = cls(0, 100, 1e-4, 1e-6, 1e-6, 1.0, 1e-6, 20.0, 3, 100000)
+        o = cls(0, 100, 1e-4, 1e-6, 1e-6, 1.0, 1e-6, 20.0, 3, 100000, 0, 0, 0.0)
         for k, v in kw.items():
             setattr(o, k, v)
         return o
@@ -54,6 +55,19 @@ def lib():
         L.oracle_volume_eval.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp]
         L.oracle_eval_plasma.argtypes = [C.c_void_p, c_dp, c_dp, C.c_double, C.c_int, c_dp]
         L.oracle_rhs.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int, c_dp, C.c_double, C.c_int, C.c_double, C.c_int, c_dp]
+        L.oracle_rhs_model.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int, c_dp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, c_dp]
+        for nm in ("oracle_expei", "oracle_gammln"):
+            getattr(L, nm).restype = C.c_double
+            getattr(L, nm).argtypes = [C.c_double]
+        L.oracle_fact.restype = C.c_double
+        L.oracle_fact.argtypes = [C.c_int]
+        L.oracle_ssbi.argtypes = [C.c_double, C.c_int, C.c_int, c_dp]
+        L.oracle_zetac.argtypes = [C.c_double, C.c_double, c_dp]
+        L.oracle_larmornumber.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.oracle_hermitian.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, c_dp]
+        L.oracle_antihermitian.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, c_dp]
+        L.oracle_warmdisp.argtypes = [C.c_double] * 5 + [C.c_int, C.c_int, C.c_int, c_dp]
+        L.oracle_warm_alpha.argtypes = [C.c_double] * 7 + [C.c_int, c_dp]
         L.oracle_abs_albajar.restype = C.c_double
         L.oracle_abs_albajar.argtypes = [c_dp, c_dp, C.c_int] + [C.c_double] * 6 + [C.c_int, C.c_double, C.c_int]
         L.oracle_besselj.restype = C.c_double
@@ -153,10 +167,11 @@ class OraclePlasma:
         lib().oracle_eval_plasma(self.h, px, pN, omega, mode, out.ctypes.data_as(c_dp))
         return dict(X=out[0], Y=out[1], N_par=out[2], b=out[3:6].copy(), Te=out[6], Lambda=out[7])
 
-    def rhs(self, u, f, mode, gl, te_min=20.0, max_harmonic=3):
+    def rhs(self, u, f, mode, gl, te_min=20.0, max_harmonic=3, absorption_model=0):
         u, pu = _d(u); t, pt = _d(gl[0]); w, pw = _d(gl[1])
         du = np.empty(7)
-        lib().oracle_rhs(self.h, pt, pw, len(t), pu, f, mode, te_min, max_harmonic, du.ctypes.data_as(c_dp))
+        lib().oracle_rhs_model(self.h, pt, pw, len(t), pu, f, mode, te_min, max_harmonic, absorption_model,
+                               du.ctypes.data_as(c_dp))
         return du
 
     def ray_init(self, x0, N0, f, mode):
@@ -215,6 +230,65 @@ class OraclePlasma:
 def abs_albajar(omega, X, Y, N_abs, N_par, Te, mode, gl, te_min=20.0, max_harmonic=3):
     t, pt = _d(gl[0]); w, pw = _d(gl[1])
     return lib().oracle_abs_albajar(pt, pw, len(t), omega, X, Y, N_abs, N_par, Te, mode, te_min, max_harmonic)
+
+
+# ---- warm-plasma absorption: reference src/general_absorption.jl ----
+def expei(x):
+    return lib().oracle_expei(float(x))
+
+
+def gammln(x):
+    return lib().oracle_gammln(float(x))
+
+
+def fact(k):
+    return lib().oracle_fact(int(k))
+
+
+def ssbi(zz, n, l):
+    out = np.zeros(l + 2)
+    k = lib().oracle_ssbi(float(zz), int(n), int(l), out.ctypes.data_as(c_dp))
+    return out[:k]
+
+
+def zetac(xi, yi):
+    out = np.zeros(2)
+    lib().oracle_zetac(float(xi), float(yi), out.ctypes.data_as(c_dp))
+    return complex(out[0], out[1])
+
+
+def larmornumber(yg, npl, mu):
+    return lib().oracle_larmornumber(float(yg), float(npl), float(mu))
+
+
+def hermitian(yg, anpl, amu, lrm, iwarm=3):
+    """rr[n + lrm, k, m] for n in -lrm..lrm, k in 0..2, m in 0..lrm."""
+    rr = np.zeros((2 * lrm + 1, 3, lrm + 1))
+    lib().oracle_hermitian(float(yg), float(anpl), float(amu), int(lrm), int(iwarm), rr.ctypes.data_as(c_dp))
+    return rr
+
+
+def antihermitian(yg, anpl, amu, lrm):
+    """ri[n - 1, k, m - 1] for n in 1..lrm, k in 0..2, m in 1..lrm."""
+    ri = np.zeros((lrm, 3, lrm))
+    lib().oracle_antihermitian(float(yg), float(anpl), float(amu), int(lrm), ri.ctypes.data_as(c_dp))
+    return ri
+
+
+def warmdisp(xg, yg, anpl, amu, anprc, sox, iwarm, lrm):
+    o = np.zeros(10)
+    lib().oracle_warmdisp(float(xg), float(yg), float(anpl), float(amu), float(anprc), int(sox), int(iwarm), int(lrm),
+                          o.ctypes.data_as(c_dp))
+    return dict(anpr=complex(o[0], o[1]), ex=complex(o[2], o[3]), ey=complex(o[4], o[5]), ez=complex(o[6], o[7]),
+                ierr=int(o[8]), iterations=int(o[9]))
+
+
+def warm_alpha(omega, X, Y, N_r, theta, te, v_g_perp, imod):
+    """α(omega, X, Y, N_r, theta, te, v_g_perp, imod) -> dict(N_warm, alpha, lrm, ierr, iterations, N_perp)."""
+    o = np.zeros(7)
+    lib().oracle_warm_alpha(float(omega), float(X), float(Y), float(N_r), float(theta), float(te), float(v_g_perp),
+                            int(imod), o.ctypes.data_as(c_dp))
+    return dict(N_warm=o[0], alpha=o[1], lrm=int(o[2]), ierr=int(o[3]), iterations=int(o[4]), N_perp=complex(o[5], o[6]))
 
 
 def tableau(scheme):

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/torj_cuda.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert tj.lib().torj_abi_version() == 2 == int(re.search(r"#define TORJ_ABI_VERSION (\d+)", hdr).group(1))
+    assert tj.lib().torj_abi_version() == 3 == int(re.search(r"#define TORJ_ABI_VERSION (\d+)", hdr).group(1))
 
 
 def test_default_options_are_the_reference_constants():
@@ -31,7 +31,7 @@ def test_default_options_are_the_reference_constants():
     assert (o.dtmax, o.abstol, o.reltol) == (1e-4, 1e-6, 1e-6)               # src/solve.jl:157
     assert (o.psi_stop, o.p_stop, o.te_min) == (1.0, 1e-6, 20.0)             # src/solve.jl:174,176; src/absorption.jl:194
     assert o.alpha_floor == 1e-14
-    assert (o.schedule, o.reserved_) == (0, 0) and C.sizeof(o) == 80
+    assert (o.schedule, o.absorption_model, o.lanes_per_ray, o.reserved_) == (0, 0, 0, 0) and C.sizeof(o) == 88
     with pytest.raises(AttributeError):
         tj.default_options(nonexistent=1)
 

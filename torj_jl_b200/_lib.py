@@ -19,7 +19,7 @@ class TorjOptions(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("n_segments", C.c_int32), ("dtmax", C.c_double), ("abstol", C.c_double),
                 ("reltol", C.c_double), ("psi_stop", C.c_double), ("p_stop", C.c_double), ("te_min", C.c_double),
                 ("max_harmonic", C.c_int32), ("max_steps_per_segment", C.c_int32), ("alpha_floor", C.c_double),
-                ("schedule", C.c_int32), ("reserved_", C.c_int32)]
+                ("schedule", C.c_int32), ("absorption_model", C.c_int32), ("lanes_per_ray", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TorjCounters(C.Structure):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "torj_ctx_launch_count": (C.c_int64, [c_vp]),
     "torj_ctx_last_trace_ms": (C.c_int, [c_vp, c_dp]),
     "torj_abs_init": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
+    "torj_warm_alpha": (C.c_int, [c_vp, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp, c_dp, c_ip, c_ip]),
     "torj_bspline_prefilter_2d": (C.c_int, [C.c_int32, C.c_int32, c_dp, c_dp]),
     "torj_bspline_prefilter_1d": (C.c_int, [C.c_int32, c_dp, c_dp]),
     "torj_plasma_create": (C.c_int, [c_vp, C.POINTER(TorjGrid), c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int32,
@@ -70,12 +71,16 @@ SIGNATURES = {
     "torj_bundle_device_profile": (c_vp, [c_vp]),
     "torj_bundle_results": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip, C.POINTER(TorjCounters)]),
     "torj_bundle_trajectories": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "torj_bundle_final_state": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp]),
+    "torj_bundle_trajectories_cyl": (C.c_int, [c_vp, c_dp, c_dp, c_dp]),
     "torj_trace": (C.c_int, [c_vp, c_vp, C.POINTER(TorjOptions), C.c_int64, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int32,
                              C.c_double, C.c_int32, c_dp, C.c_int32, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip, c_ip, C.c_int64, C.c_int64,
                              C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, C.POINTER(TorjCounters)]),
     "torj_multi_create": (C.c_int, [C.c_int32, C.POINTER(c_vp)]),
     "torj_multi_destroy": (None, [c_vp]),
     "torj_multi_device_count": (C.c_int32, [c_vp]),
+    "torj_multi_configure": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int32]),
+    "torj_multi_used_nccl": (C.c_int32, [c_vp]),
     "torj_multi_abs_init": (C.c_int, [c_vp, C.c_int32, c_dp, c_dp]),
     "torj_multi_plasma_create_from_data": (C.c_int, [c_vp, C.POINTER(TorjGrid), c_dp, c_dp, c_dp, c_dp, C.c_int32, c_dp, c_dp,
                                                      c_dp, c_dp, c_dp, C.c_int32, C.POINTER(c_vp)]),

@@ -2,8 +2,15 @@
 // Plain CUDA runtime; no torch types, no CPU fallback (every entry point needs a CUDA device).
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdio>
 #include <memory>
 #include <cstring>
@@ -41,7 +48,17 @@ struct torj_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the last k_trace launch
     bool ev_valid = false;
     struct torj_bundle* ws = nullptr;  // workspace of the one-shot torj_trace call, kept between calls
+    double2* d_warm_tab = nullptr;     // set_extv! tables of the warm-plasma model (reference src/general_absorption.jl:8-13)
 };
+
+// The Gauss-Legendre table lives in ONE __constant__ symbol per device (like the reference's module globals,
+// src/constants.jl:7-8); this registry remembers what each device holds so that a second context on the device inherits
+// it, identical re-initialisations are free, and a different table is written only after the whole device is idle.
+struct GLRegistry {
+    std::mutex mu;
+    std::vector<std::vector<double>> tab;  // per device: n nodes then n weights; empty = never set
+};
+static GLRegistry g_gl;
 
 static std::atomic<uint64_t> g_plasma_serial{0};  // torj_multi_* creates plasmas from one host thread per device
 
@@ -67,6 +84,7 @@ struct torj_bundle {
     double *d_pos = nullptr, *d_dir = nullptr, *d_w = nullptr, *d_freq = nullptr, *d_u0 = nullptr, *d_s0 = nullptr,
            *d_psil = nullptr, *d_Pf = nullptr, *d_Pdep = nullptr;
     int *d_mode = nullptr, *d_status = nullptr, *d_npts = nullptr;
+    double* d_ufinal = nullptr;  // [7][n] state at retirement
     // deposition
     int n_psi = 0;
     double *d_edges = nullptr, *d_bins = nullptr, *d_dV = nullptr, *d_profile = nullptr;
@@ -133,6 +151,8 @@ void torj_options_default(torj_options* o) {
     o->te_min = 20.0;
     o->max_harmonic = 3;
     o->schedule = 0;
+    o->absorption_model = 0;
+    o->lanes_per_ray = 0;
     o->reserved_ = 0;
     o->max_steps_per_segment = 100000;
     o->alpha_floor = 1e-14;
@@ -157,6 +177,57 @@ static void fill_tableaux(Tableau t[2]) {
     a[2][0] = -68.0 / 375.0; a[2][1] = 368.0 / 375.0;
     a[3][0] = 31.0 / 144.0; a[3][1] = 529.0 / 1152.0; a[3][2] = 125.0 / 384.0;
     t[1].bt[0] = 25.0 / 144.0; t[1].bt[1] = -575.0 / 1152.0; t[1].bt[2] = 125.0 / 384.0;
+}
+
+// Warm-plasma model: quadrature tables of set_extv! (reference src/general_absorption.jl:8-13, src/constants.jl:1-4), the
+// combination weights of dieltens_maxw_fr (:1069,1081-1082), fact (:240-257) and 1/exp(gammln(m + 3/2)) with the
+// reference's own 6-term Lanczos gammln (:265-283) — restated here because ssbi (:298) takes its Gamma values from it.
+static double ref_fact(int k) {
+    double r = 1.0;
+    for (int i = 2; i <= k; ++i) r *= (double)i;
+    return r;
+}
+static double ref_gammln(double x) {
+    const double stp = 2.5066282746310005;
+    const double cof[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2,
+                           -0.5395239384953e-5};
+    double y = x, tmp = x + 5.5;
+    tmp = (x + 0.5) * std::log(tmp) - tmp;
+    double ser = 1.000000000190015;
+    for (int j = 0; j < 6; ++j) { y = y + 1.0; ser = ser + cof[j] / y; }
+    return tmp + std::log(stp * ser / x);
+}
+static int upload_warm_constants(torj_ctx* c) {
+    const int ntv = TORJ_WARM_NTV;
+    const double tmax = 5.0, dt = 2.0 * tmax / (ntv - 1);
+    std::vector<double2> tab(ntv);
+    for (int i = 1; i <= ntv; ++i) {
+        const double t = -tmax + (i - 1) * dt;
+        tab[i - 1] = make_double2(t, std::exp(-(t * t)) * dt);
+    }
+    CK(cudaMalloc(&c->d_warm_tab, ntv * sizeof(double2)));
+    CK(cudaMemcpy(c->d_warm_tab, tab.data(), ntv * sizeof(double2), cudaMemcpyHostToDevice));
+    double comb[6][6][6], fal[6], fct[8], igam[8];
+    memset(comb, 0, sizeof comb);
+    for (int l = 1; l <= 5; ++l) {
+        const int lm = l - 1;
+        fal[l] = -std::pow(0.25, l) * ref_fact(2 * l) / (ref_fact(l) * ref_fact(l));
+        for (int is = 0; is <= l; ++is) {
+            const int k = l - is;
+            const double asl = ((k % 2) ? -1.0 : 1.0) / (ref_fact(is + l) * ref_fact(l - is));
+            const double bsl = asl * (is * is + (double)(2 * k * lm * (l + is)) / (2 * l - 1));
+            double* cb = comb[is][l];
+            cb[0] = (double)(is * is) * asl; cb[1] = (double)(is * l) * asl; cb[2] = bsl;
+            cb[3] = (double)is * asl; cb[4] = (double)l * asl; cb[5] = asl;
+        }
+    }
+    fal[0] = 0.0;
+    for (int m = 0; m < 8; ++m) { fct[m] = ref_fact(m); igam[m] = 1.0 / std::exp(ref_gammln(m + 1.5)); }
+    CK(cudaMemcpyToSymbol(cw_comb, comb, sizeof comb));
+    CK(cudaMemcpyToSymbol(cw_fal, fal, sizeof fal));
+    CK(cudaMemcpyToSymbol(cw_fact, fct, sizeof fct));
+    CK(cudaMemcpyToSymbol(cw_igam, igam, sizeof igam));
+    return 0;
 }
 
 int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
@@ -202,6 +273,11 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
         for (int j = 0; j <= 13; ++j) ce[3 + j] = inv[13 - j];
         CK(cudaMemcpyToSymbol(c_exp, ce, sizeof ce));
     }
+    if (int rc = upload_warm_constants(c)) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_gl.mu);
+        if ((int)g_gl.tab.size() > device && !g_gl.tab[device].empty()) c->gl_set = true;  // inherited (see GLRegistry)
+    }
     *out = guard.release();
     return 0;
 }
@@ -209,6 +285,7 @@ int torj_ctx_create(int device, void* cuda_stream, torj_ctx** out) {
 void torj_ctx_destroy(torj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaFree(c->d_warm_tab);
     if (c->ws) torj_bundle_destroy(c->ws);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -236,7 +313,16 @@ int torj_ctx_last_trace_ms(torj_ctx* c, double* ms) {
 
 int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* weights) {
     if (n < 1 || n > TORJ_MAX_GL) FAIL("torj_abs_init: need 1 <= n <= 64");
+    if (!nodes || !weights) FAIL("torj_abs_init: NULL nodes / weights");
     if (set_device(c)) return 1;
+    std::vector<double> want(nodes, nodes + n);
+    want.insert(want.end(), weights, weights + n);
+    std::lock_guard<std::mutex> lk(g_gl.mu);
+    if ((int)g_gl.tab.size() <= c->device) g_gl.tab.resize(c->device + 1);
+    if (g_gl.tab[c->device] == want) {  // the device already holds exactly this table
+        c->gl_set = true;
+        return 0;
+    }
     GLNodes g;
     memset(&g, 0, sizeof g);
     g.n = n;
@@ -245,8 +331,9 @@ int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* wei
         g.w[i] = weights[i];
         g.sq[i] = std::sqrt(1.0 - nodes[i] * nodes[i]);
     }
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaDeviceSynchronize());  // no kernel of ANY context on this device may be reading the old table
     CK(cudaMemcpyToSymbol(c_gl, &g, sizeof g));
+    g_gl.tab[c->device] = want;
     c->gl_set = true;
     return 0;
 }
@@ -500,7 +587,10 @@ int torj_probe(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
     double *dx = o_x.get(), *dN = o_N.get(), *dout = o_out.get();
     CK(cudaMemcpyAsync(dx, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dN, N, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_probe<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, dout);
+    const int model = opt ? opt->absorption_model : 0;
+    if (model != 0 && model != 1) FAIL("torj_probe: absorption_model must be 0 (Albajar) or 1 (warm)");
+    k_probe<<<(unsigned)((n + 127) / 128), 128, TORJ_WARM_H * 128 * sizeof(double), c->stream>>>(
+        p->T, n, dx, dN, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, model, c->d_warm_tab, dout);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout, 11 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -518,11 +608,40 @@ int torj_rhs(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t
     CK(dev_alloc(o_du, 7 * (size_t)n));
     double *d_u = o_u.get(), *d_du = o_du.get();
     CK(cudaMemcpyAsync(d_u, u, 7 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    k_rhs<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, d_du);
+    const int model = opt ? opt->absorption_model : 0;
+    if (model != 0 && model != 1) FAIL("torj_rhs: absorption_model must be 0 (Albajar) or 1 (warm)");
+    k_rhs<<<(unsigned)((n + 127) / 128), 128, TORJ_WARM_H * 128 * sizeof(double), c->stream>>>(
+        p->T, n, d_u, freq_hz, mode, so.te_min, so.max_harmonic, so.alpha_floor, model, c->d_warm_tab, d_du);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(du, d_du, 7 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int torj_warm_alpha(torj_ctx* c, int64_t n, const double* omega, const double* X, const double* Y, const double* N_r,
+                    const double* theta, const double* te, const double* v_g_perp, int32_t imod, double* N_warm,
+                    double* alpha, int32_t* lrm, int32_t* ierr) {
+    if (!c || n < 1 || !omega || !X || !Y || !N_r || !theta || !te || !v_g_perp) FAIL("torj_warm_alpha: bad argument");
+    if (set_device(c)) return 1;
+    std::vector<double> in(7 * (size_t)n), out(5 * (size_t)n);
+    const double* src[7] = {omega, X, Y, N_r, theta, te, v_g_perp};
+    for (int q = 0; q < 7; ++q) memcpy(in.data() + q * n, src[q], n * sizeof(double));
+    dev_ptr<double> o_in, o_out;
+    CK(dev_alloc(o_in, in.size()));
+    CK(dev_alloc(o_out, out.size()));
+    CK(cudaMemcpyAsync(o_in.get(), in.data(), in.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_warm_alpha<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, o_in.get(), imod, c->d_warm_tab, o_out.get());
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out.data(), o_out.get(), out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        if (N_warm) N_warm[i] = out[i];
+        if (alpha) alpha[i] = out[n + i];
+        if (lrm) lrm[i] = (int32_t)out[2 * n + i];
+        if (ierr) ierr[i] = (int32_t)out[3 * n + i];
+    }
     return 0;
 }
 
@@ -569,6 +688,7 @@ int torj_bundle_create(torj_ctx* c, int64_t n, const double* pos, const double* 
     CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
     CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_ufinal, 7 * n * sizeof(double)));
     BundleDev& B = b->B;
     B.n_rays = n; B.pos = b->d_pos; B.dir = b->d_dir; B.weight = b->d_w; B.freq = b->d_freq; B.mode = b->d_mode;
     B.per_ray_fm = per_ray_fm; B.u0 = b->d_u0; B.s0 = b->d_s0; B.psi_launch = b->d_psil; B.status = b->d_status;
@@ -625,6 +745,7 @@ int torj_bundle_create_from_launchers(torj_ctx* c, int32_t n_launchers, const do
     CK(cudaMalloc(&b->d_npts, n * sizeof(int)));
     CK(cudaMalloc(&b->d_queue, sizeof(unsigned long long)));
     CK(cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&b->d_ufinal, 7 * n * sizeof(double)));
     CK(cudaMalloc(&b->d_beam, n * sizeof(int)));
     b->n_beams = n_launchers;
     BundleDev& B = b->B;
@@ -684,22 +805,24 @@ void torj_bundle_destroy(torj_bundle* b) {
     cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
     cudaFree(b->d_profile);
     cudaFree(b->d_beam);
+    cudaFree(b->d_ufinal);
     free_traj(b);
     delete b;
 }
 
 int torj_bundle_set_window(torj_bundle* b, int64_t first, int64_t count, int32_t max_pts) {
+    if (count > 0 && max_pts > 0 && (first < 0 || first + count > b->n)) FAIL("torj_bundle_set_window: window outside the bundle");
     if (set_device(b->ctx)) return 1;
     CK(cudaStreamSynchronize(b->ctx->stream));
     free_traj(b);
-    if (count <= 0 || max_pts <= 0) { b->traj_first = 0; b->traj_count = 0; b->traj_max = 0; return 0; }
-    if (first < 0 || first + count > b->n) FAIL("torj_bundle_set_window: window outside the bundle");
-    b->traj_first = first; b->traj_count = count; b->traj_max = max_pts;
+    b->traj_first = 0; b->traj_count = 0; b->traj_max = 0;  // a failing allocation below leaves an EMPTY window, not a dangling one
+    if (count <= 0 || max_pts <= 0) return 0;
     size_t m = (size_t)count * max_pts;
     CK(cudaMalloc(&b->d_ts, m * sizeof(double)));
     CK(cudaMalloc(&b->d_txyz, 3 * m * sizeof(double)));
     CK(cudaMalloc(&b->d_tP, m * sizeof(double)));
     CK(cudaMalloc(&b->d_tdP, m * sizeof(double)));
+    b->traj_first = first; b->traj_count = count; b->traj_max = max_pts;
     return 0;
 }
 
@@ -736,6 +859,9 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (!(od.dtmax > 0.0) || !(od.abstol > 0.0) || !(od.reltol > 0.0)) FAIL("torj_bundle_trace: dtmax, abstol and reltol must be > 0");
     if (od.schedule < 0 || od.schedule > 2) FAIL("torj_bundle_trace: schedule must be 0 (automatic), 1 (whole rays) or 2 (segment hand-off)");
     if (od.max_steps_per_segment < 1) FAIL("torj_bundle_trace: max_steps_per_segment < 1");
+    if (od.absorption_model != 0 && od.absorption_model != 1) FAIL("torj_bundle_trace: absorption_model must be 0 (Albajar) or 1 (warm)");
+    if (od.lanes_per_ray != 0 && od.lanes_per_ray != 1 && od.lanes_per_ray != 32) FAIL("torj_bundle_trace: lanes_per_ray must be 0 (automatic), 1 or 32");
+    if (od.absorption_model == 1 && od.max_harmonic > 3) FAIL("torj_bundle_trace: max_harmonic > 3 belongs to the Albajar model; the warm model takes its harmonics from larmornumber");
     if (!(s_max > 0.0)) FAIL("torj_bundle_trace: s_max must be > 0");
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
@@ -784,7 +910,17 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.J.first = b->traj_first; a.J.count = b->traj_count; a.J.max_pts = b->traj_max;
     a.J.s = b->d_ts; a.J.xyz = b->d_txyz; a.J.P = b->d_tP; a.J.dP = b->d_tdP; a.J.prof = b->d_tprof;
     a.n_psi = n_psi; a.n_beams = b->n_beams; a.beam_id = b->d_beam; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
+    a.warm_tab = c->d_warm_tab; a.u_final = b->d_ufinal;
+    const int model = od.absorption_model;
+    // A warp per ray (lanes_per_ray = 32) when the bundle is far too small to fill the GPU with one thread per ray —
+    // then the time is one ray's latency, and splitting the quadrature nodes over 32 lanes shortens exactly that — and
+    // for the warm model up to one ray per resident lane: its alpha is ~100x the rest of the RHS and warp-cooperative
+    // either way, so a warp per ray loses little throughput and gains the latency.
+    const int64_t lanes_guess = (int64_t)c->num_sms * TORJ_MINB * TORJ_TPB;
+    int coop = od.lanes_per_ray == 32;
+    if (od.lanes_per_ray == 0) coop = model == 1 ? (b->n <= lanes_guess / 2) : (b->n * 16 <= lanes_guess);
     size_t smem = (size_t)n_psi * sizeof(double);
+    if (model == 1 && !coop) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
 #if TORJ_K_SMEM
     smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
 #endif
@@ -792,11 +928,17 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     smem += (size_t)TORJ_PARK_SLOTS * TORJ_TPB * sizeof(double);
 #endif
     int bps = 0;
-    int64_t warps = (b->n + 31) / 32;
+    int64_t warps = coop ? b->n : (b->n + 31) / 32;
     int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);
-    // harmonics above the third run in their own instantiations, so the default kernels do not carry the code
-    void (*kern)(TraceArgs) = od.max_harmonic > 3 ? (od.scheme == 0 ? k_trace<0, true> : k_trace<1, true>)
-                                                  : (od.scheme == 0 ? k_trace<0, false> : k_trace<1, false>);
+    // harmonics above the third, the warm model and the warp-per-ray mapping run in their own instantiations, so the
+    // default kernels do not carry the code
+    void (*kern)(TraceArgs);
+    const bool high = od.max_harmonic > 3, z3 = od.scheme == 1;
+    if (model == 1) kern = coop ? (z3 ? k_trace<1, false, 1, true> : k_trace<0, false, 1, true>)
+                                : (z3 ? k_trace<1, false, 1, false> : k_trace<0, false, 1, false>);
+    else if (coop) kern = high ? (z3 ? k_trace<1, true, 0, true> : k_trace<0, true, 0, true>)
+                               : (z3 ? k_trace<1, false, 0, true> : k_trace<0, false, 0, true>);
+    else kern = high ? (z3 ? k_trace<1, true> : k_trace<0, true>) : (z3 ? k_trace<1, false> : k_trace<0, false>);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TORJ_TPB, smem));
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
@@ -805,7 +947,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     // rays on 37 888 lanes: 1.73 ray-times instead of 2) and keeps the lanes of a warp in step: with whole rays per lane
     // a bundle of rays of very different lengths (the 1 M-ray angle sweep) drifts apart and some lane pays for the full
     // absorption coefficient on every trip (measured 3.1 s -> 2.4 s). Below one wave there is nothing to balance.
-    const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB;
+    const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB / (coop ? 32 : 1);  // rays in flight
     int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes);
     if (od.n_segments < 2 || b->n > 0x7fffffff) interleave = 0;
     a.interleave = interleave; a.hand = nullptr; a.seg_done = nullptr; a.rays_left = nullptr;
@@ -887,6 +1029,50 @@ int torj_bundle_trajectories(torj_bundle* b, double* s, double* xyz, double* P, 
     return 0;
 }
 
+int torj_bundle_final_state(torj_bundle* b, double* u_final, double* R, double* phi, double* tau) {
+    torj_ctx* c = b->ctx;
+    if (b->n_psi == 0) FAIL("torj_bundle_final_state: nothing traced yet");
+    if (set_device(c)) return 1;
+    const int64_t n = b->n;
+    std::vector<double> u(7 * (size_t)n);
+    std::vector<int> st(n);
+    CK(cudaMemcpyAsync(u.data(), b->d_ufinal, u.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.data(), b->d_status, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const double nan = std::nan("");
+    for (int64_t i = 0; i < n; ++i) {
+        const bool never_traced = st[i] == TORJ_RAY_CUTOFF_AT_ENTRY || st[i] == TORJ_RAY_INIT_FAILED;
+        if (never_traced) for (int q = 0; q < 7; ++q) u[(size_t)q * n + i] = nan;
+        const double x = u[i], y = u[n + i], P = u[6 * (size_t)n + i];
+        if (R) R[i] = std::hypot(x, y);
+        if (phi) phi[i] = std::atan2(y, x);
+        if (tau) tau[i] = -std::log(P);
+    }
+    if (u_final) memcpy(u_final, u.data(), u.size() * sizeof(double));
+    return 0;
+}
+
+int torj_bundle_trajectories_cyl(torj_bundle* b, double* R, double* phi, double* tau) {
+    if (b->traj_count <= 0) FAIL("torj_bundle_trajectories_cyl: no trajectory window set");
+    const size_t m = (size_t)b->traj_count * b->traj_max;
+    std::vector<double> xyz(3 * m), P(m);
+    if (int rc = torj_bundle_trajectories(b, nullptr, xyz.data(), P.data(), nullptr, nullptr)) return rc;
+    std::vector<int> np(b->n);
+    CK(cudaMemcpy(np.data(), b->d_npts, b->n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < b->traj_count; ++r) {
+        const int cnt = std::min<int>(std::max(np[b->traj_first + r], 0), b->traj_max);
+        const double* x = xyz.data() + (size_t)r * 3 * b->traj_max;
+        for (int k = 0; k < b->traj_max; ++k) {
+            const size_t o = (size_t)r * b->traj_max + k;
+            const bool ok = k < cnt;
+            if (R) R[o] = ok ? std::hypot(x[k], x[b->traj_max + k]) : 0.0;
+            if (phi) phi[o] = ok ? std::atan2(x[b->traj_max + k], x[k]) : 0.0;
+            if (tau) tau[o] = ok ? -std::log(P[o]) : 0.0;
+        }
+    }
+    return 0;
+}
+
 int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64_t n_rays, const double* pos,
                const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
                double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id, double* dP_dV,
@@ -925,12 +1111,127 @@ int torj_trace(torj_ctx* c, const torj_plasma* p, const torj_options* opt, int64
 }
 
 // ---- single-process multi-GPU front end (what a Julia make_beam on an 8-GPU box calls) -------------------------
+// NCCL is loaded at run time (dlopen of libnccl.so.2: a process that already holds a copy, e.g. PyTorch's, keeps using
+// that one) — nccl.h supplies only the types. Without the library the front end still works through the host sum.
+}  // extern "C" (C++ helpers of the multi-GPU front end follow)
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            api.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (api.h) break;
+        }
+        if (!api.h) return;
+        api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.h, "ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+        api.ok = api.CommInitAll && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    });
+    return api;
+}
+
+// One persistent host thread per device: jobs are closures run in order; run() hands one job to every worker and waits.
+struct MultiWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false, done = true;
+    void loop() {
+        for (;;) {
+            std::function<void()> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return has_job || quit; });
+                if (quit && !has_job) return;
+                j = std::move(job);
+                has_job = false;
+            }
+            j();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                done = true;
+            }
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> j) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = std::move(j);
+            has_job = true;
+            done = false;
+        }
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+    }
+};
+
+// Pinned host staging of one device's shard, grown on demand and kept between calls
+struct MultiStage {
+    size_t cap = 0;
+    double *pos = nullptr, *dir = nullptr, *w = nullptr, *freq = nullptr, *Pf = nullptr, *Pd = nullptr;
+    int *mode = nullptr, *beam = nullptr, *np = nullptr, *st = nullptr;
+    std::vector<int64_t> gidx;  // global ray index of local ray j
+    void release() {
+        cudaFreeHost(pos); cudaFreeHost(dir); cudaFreeHost(w); cudaFreeHost(freq); cudaFreeHost(Pf); cudaFreeHost(Pd);
+        cudaFreeHost(mode); cudaFreeHost(beam); cudaFreeHost(np); cudaFreeHost(st);
+        pos = dir = w = freq = Pf = Pd = nullptr; mode = beam = np = st = nullptr; cap = 0;
+    }
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e;
+        if ((e = cudaHostAlloc(&pos, 3 * n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&dir, 3 * n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&w, n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&freq, n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&Pf, n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&Pd, n * sizeof(double), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&mode, n * sizeof(int), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&beam, n * sizeof(int), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&np, n * sizeof(int), cudaHostAllocDefault))) return e;
+        if ((e = cudaHostAlloc(&st, n * sizeof(int), cudaHostAllocDefault))) return e;
+        cap = n;
+        return cudaSuccess;
+    }
+};
+
 struct torj_multi {
     std::vector<torj_ctx*> ctx;
+    std::vector<std::unique_ptr<MultiWorker>> worker;
+    std::vector<MultiStage> stage;
+    std::vector<ncclComm_t> comm;  // empty when NCCL is unavailable
+    int sharding = 0;              // 0 contiguous, 1 block-cyclic
+    int64_t block = 1;
+    int reduction = 0;             // 0 NCCL all-reduce (host sum when unavailable), 1 host sum in device order
+    int used_nccl = 0;
+    template <class F>
+    void run(int used, F&& f) {  // f(d) on worker d for d < used, all concurrently
+        for (int d = 0; d < used; ++d) worker[d]->submit([&f, d] { f(d); });
+        for (int d = 0; d < used; ++d) worker[d]->wait();
+    }
 };
 struct torj_mplasma {
     std::vector<torj_plasma*> p;
 };
+
+extern "C" {
 
 int torj_multi_create(int32_t n_devices, torj_multi** out) {
     if (!out) FAIL("torj_multi_create: out is NULL");
@@ -942,22 +1243,58 @@ int torj_multi_create(int32_t n_devices, torj_multi** out) {
     }
     if (n_devices <= 0 || n_devices > ndev) n_devices = ndev;
     torj_multi* m = new torj_multi();
+    Guard<torj_multi, torj_multi_destroy> guard(m);
     for (int d = 0; d < n_devices; ++d) {
         torj_ctx* c = nullptr;
-        if (torj_ctx_create(d, nullptr, &c)) { for (auto* q : m->ctx) torj_ctx_destroy(q); delete m; return 1; }
+        if (int rc = torj_ctx_create(d, nullptr, &c)) return rc;
         m->ctx.push_back(c);
     }
-    *out = m;
+    m->stage.resize(n_devices);
+    for (int d = 0; d < n_devices; ++d) {
+        m->worker.emplace_back(new MultiWorker());
+        MultiWorker* w = m->worker.back().get();
+        w->th = std::thread([w] { w->loop(); });
+    }
+    if (n_devices > 1 && nccl_api().ok) {  // one communicator per device, created once
+        std::vector<int> devs(n_devices);
+        for (int d = 0; d < n_devices; ++d) devs[d] = d;
+        m->comm.resize(n_devices);
+        ncclResult_t r = nccl_api().CommInitAll(m->comm.data(), n_devices, devs.data());
+        if (r != ncclSuccess) m->comm.clear();  // fall back to the host sum; torj_multi_used_nccl reports it
+    }
+    *out = guard.release();
     return 0;
 }
 
 void torj_multi_destroy(torj_multi* m) {
     if (!m) return;
+    for (auto& w : m->worker) {
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->quit = true;
+        }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    for (size_t d = 0; d < m->comm.size(); ++d) nccl_api().CommDestroy(m->comm[d]);
+    for (size_t d = 0; d < m->stage.size(); ++d) {
+        if (d < m->ctx.size()) cudaSetDevice(m->ctx[d]->device);
+        m->stage[d].release();
+    }
     for (auto* c : m->ctx) torj_ctx_destroy(c);
     delete m;
 }
 
 int32_t torj_multi_device_count(const torj_multi* m) { return (int32_t)m->ctx.size(); }
+int32_t torj_multi_used_nccl(const torj_multi* m) { return m->used_nccl; }
+
+int torj_multi_configure(torj_multi* m, int32_t sharding, int64_t block_rays, int32_t reduction) {
+    if (sharding != 0 && sharding != 1) FAIL("torj_multi_configure: sharding must be 0 (contiguous) or 1 (block-cyclic)");
+    if (sharding == 1 && block_rays < 1) FAIL("torj_multi_configure: block_rays < 1");
+    if (reduction != 0 && reduction != 1) FAIL("torj_multi_configure: reduction must be 0 (NCCL all-reduce) or 1 (host sum)");
+    m->sharding = sharding; m->block = std::max<int64_t>(1, block_rays); m->reduction = reduction;
+    return 0;
+}
 
 int torj_multi_abs_init(torj_multi* m, int32_t n, const double* nodes, const double* weights) {
     for (auto* c : m->ctx)
@@ -988,8 +1325,23 @@ void torj_multi_plasma_destroy(torj_mplasma* mp) {
     delete mp;
 }
 
-// Rays are split into contiguous blocks, one per device, traced concurrently by one host thread per device; profiles
-// and deposited power are summed on the host in device order (deterministic), per-ray outputs land in their slices.
+// The rays of shard d of `used`: contiguous block, or the blocks d, d+used, d+2 used, ... of `block` rays each.
+static void shard_indices(int64_t n_rays, int used, int d, int sharding, int64_t block, std::vector<int64_t>& idx) {
+    idx.clear();
+    if (sharding == 0) {
+        const int64_t base = n_rays / used, rem = n_rays % used;
+        const int64_t lo = d * base + std::min<int64_t>(d, rem), n = base + (d < rem ? 1 : 0);
+        idx.resize(n);
+        for (int64_t j = 0; j < n; ++j) idx[j] = lo + j;
+    } else {
+        const int64_t nb = (n_rays + block - 1) / block;
+        for (int64_t bk = d; bk < nb; bk += used)
+            for (int64_t g = bk * block; g < std::min(n_rays, (bk + 1) * block); ++g) idx.push_back(g);
+    }
+}
+
+// Phase A on device d: gather the shard into pinned staging, upload, enqueue ray init + trace + finalize.
+// Phase B: (NCCL all-reduce of the device profile buffers, in place, one call per device thread;) results to the host.
 int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* opt, int64_t n_rays, const double* pos,
                      const double* dir, const double* weight, const double* freq_hz, const int32_t* mode, int32_t per_ray_fm,
                      double s_max, int32_t n_psi, const double* psi_edges, int32_t n_beams, const int32_t* beam_id,
@@ -1000,43 +1352,128 @@ int torj_multi_trace(torj_multi* m, const torj_mplasma* mp, const torj_options* 
     if ((int)mp->p.size() != nd) FAIL("torj_multi_trace: plasma was created on a different device set");
     if (n_rays < 1) FAIL("torj_multi_trace: n_rays < 1");
     if (n_beams < 1 || !beam_id) n_beams = 1;
-    const int used = (int)std::min<int64_t>(nd, n_rays);
+    if (traj_count < 0 || (traj_count > 0 && (traj_first < 0 || traj_first + traj_count > n_rays)))
+        FAIL("torj_multi_trace: trajectory window outside the bundle");
+    int used = (int)std::min<int64_t>(nd, n_rays);
+    if (m->sharding == 1) used = (int)std::min<int64_t>(used, (n_rays + m->block - 1) / m->block);
     std::vector<int> rcs(used, 0);
     std::vector<std::string> errs(used);
-    std::vector<std::vector<double>> prof(used), dep(used);
     std::vector<torj_counters> cnts(used);
-    std::vector<std::thread> th;
-    const int64_t base = n_rays / used, rem = n_rays % used;
-    for (int d = 0; d < used; ++d) {
-        th.emplace_back([&, d]() {
-            const int64_t lo = d * base + std::min<int64_t>(d, rem), n = base + (d < rem ? 1 : 0);
-            std::vector<double> p3(3 * n), d3(3 * n);
-            for (int c = 0; c < 3; ++c) {
-                memcpy(p3.data() + c * n, pos + c * n_rays + lo, n * sizeof(double));
-                memcpy(d3.data() + c * n, dir + c * n_rays + lo, n * sizeof(double));
+    std::vector<int64_t> wlo(used, 0), wcnt(used, 0);  // local trajectory window of each shard
+    const size_t prow = (size_t)n_psi + 2;
+    const bool want_nccl = m->reduction == 0 && used == nd && (int)m->comm.size() == nd && nd > 1;
+    std::vector<std::vector<double>> prof(used);
+
+    // ---- phase A
+    m->run(used, [&](int d) {
+        torj_ctx* c = m->ctx[d];
+        MultiStage& S = m->stage[d];
+        auto fail = [&](int rc) { rcs[d] = rc; errs[d] = g_err; };  // g_err is thread-local
+        if (set_device(c)) return fail(1);
+        shard_indices(n_rays, used, d, m->sharding, m->block, S.gidx);
+        const int64_t n = (int64_t)S.gidx.size();
+        if (cudaError_t e = S.reserve((size_t)n)) { g_err = std::string("pinned staging: ") + cudaGetErrorString(e); return fail(1); }
+        for (int64_t j = 0; j < n; ++j) {
+            const int64_t g = S.gidx[j];
+            for (int q = 0; q < 3; ++q) { S.pos[q * n + j] = pos[q * n_rays + g]; S.dir[q * n + j] = dir[q * n_rays + g]; }
+            S.w[j] = weight[g];
+            if (per_ray_fm) { S.freq[j] = freq_hz[g]; S.mode[j] = mode[g]; }
+            if (n_beams > 1) S.beam[j] = beam_id[g];
+        }
+        if (!per_ray_fm) { S.freq[0] = freq_hz[0]; S.mode[0] = mode[0]; }
+        // local trajectory window: the local rays whose global index falls into [traj_first, traj_first + traj_count)
+        int64_t lo = n, cntw = 0;
+        if (traj_count > 0)
+            for (int64_t j = 0; j < n; ++j)
+                if (S.gidx[j] >= traj_first && S.gidx[j] < traj_first + traj_count) { lo = std::min(lo, j); ++cntw; }
+        wlo[d] = cntw ? lo : 0; wcnt[d] = cntw;  // contiguous in local order for both shardings
+        torj_bundle* b = c->ws;
+        if (b && (b->n != n || b->per_ray_fm != per_ray_fm)) { torj_bundle_destroy(b); b = c->ws = nullptr; }
+        int rc = 0;
+        if (!b) {
+            rc = torj_bundle_create(c, n, S.pos, S.dir, S.w, S.freq, S.mode, per_ray_fm, &b);
+            if (rc) return fail(rc);
+            c->ws = b;
+        } else if ((rc = bundle_upload(b, S.pos, S.dir, S.w, S.freq, S.mode))) {
+            return fail(rc);
+        }
+        if (wcnt[d] != b->traj_count || wlo[d] != b->traj_first || (wcnt[d] > 0 && traj_max_pts != b->traj_max))
+            rc = torj_bundle_set_window(b, wlo[d], wcnt[d], traj_max_pts);
+        if (!rc) rc = torj_bundle_set_beams(b, n_beams, n_beams > 1 ? S.beam : nullptr);
+        if (!rc) rc = torj_bundle_trace(b, mp->p[d], opt, s_max, n_psi, psi_edges);
+        if (rc) fail(rc);
+    });
+    bool all_ok = true;
+    for (int d = 0; d < used; ++d) all_ok = all_ok && rcs[d] == 0;
+
+    // ---- phase B (the collective only when every device got through phase A: a missing rank would hang the others)
+    const bool do_nccl = all_ok && want_nccl;
+    if (all_ok) m->run(used, [&](int d) {
+        torj_ctx* c = m->ctx[d];
+        torj_bundle* b = c->ws;
+        MultiStage& S = m->stage[d];
+        auto fail = [&](int rc) { rcs[d] = rc; errs[d] = g_err; };
+        if (set_device(c)) return fail(1);
+        const int64_t n = b->n;
+        if (do_nccl) {
+            ncclResult_t r = nccl_api().AllReduce(b->d_profile, b->d_profile, (size_t)n_beams * prow, ncclDouble, ncclSum,
+                                                  m->comm[d], c->stream);
+            if (r != ncclSuccess) { g_err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r); return fail(3); }
+        }
+        memset(&cnts[d], 0, sizeof(torj_counters));
+        prof[d].assign((size_t)n_beams * prow, 0.0);
+        std::vector<double> pr((size_t)n_beams * n_psi), dp(n_beams);
+        int rc = torj_bundle_results(b, (!do_nccl || d == 0) ? pr.data() : nullptr, (!do_nccl || d == 0) ? dp.data() : nullptr,
+                                     P_final ? S.Pf : nullptr, P_dep ? S.Pd : nullptr, n_points ? S.np : nullptr,
+                                     status ? S.st : nullptr, &cnts[d]);
+        if (rc) return fail(rc);
+        for (int q = 0; q < n_beams; ++q) {
+            memcpy(prof[d].data() + q * prow, pr.data() + (size_t)q * n_psi, n_psi * sizeof(double));
+            prof[d][q * prow + n_psi] = dp[q];
+        }
+        for (int64_t j = 0; j < n; ++j) {
+            const int64_t g = S.gidx[j];
+            if (P_final) P_final[g] = S.Pf[j];
+            if (P_dep) P_dep[g] = S.Pd[j];
+            if (n_points) n_points[g] = S.np[j];
+            if (status) status[g] = S.st[j];
+        }
+        if (wcnt[d] > 0) {
+            const size_t M = (size_t)traj_max_pts, wc = (size_t)wcnt[d];
+            std::vector<double> ts(traj_s ? wc * M : 0), tx(traj_xyz ? 3 * wc * M : 0), tp(traj_P ? wc * M : 0),
+                td(traj_dP_ds ? wc * M : 0), tv(traj_dP_dV_ray ? wc * n_psi : 0);
+            rc = torj_bundle_trajectories(b, traj_s ? ts.data() : nullptr, traj_xyz ? tx.data() : nullptr,
+                                          traj_P ? tp.data() : nullptr, traj_dP_ds ? td.data() : nullptr,
+                                          traj_dP_dV_ray ? tv.data() : nullptr);
+            if (rc) return fail(rc);
+            for (size_t k = 0; k < wc; ++k) {
+                const size_t o = (size_t)(S.gidx[wlo[d] + k] - traj_first);
+                if (traj_s) memcpy(traj_s + o * M, ts.data() + k * M, M * sizeof(double));
+                if (traj_xyz) memcpy(traj_xyz + o * 3 * M, tx.data() + k * 3 * M, 3 * M * sizeof(double));
+                if (traj_P) memcpy(traj_P + o * M, tp.data() + k * M, M * sizeof(double));
+                if (traj_dP_ds) memcpy(traj_dP_ds + o * M, td.data() + k * M, M * sizeof(double));
+                if (traj_dP_dV_ray) memcpy(traj_dP_dV_ray + o * n_psi, tv.data() + k * n_psi, n_psi * sizeof(double));
             }
-            prof[d].assign((size_t)n_beams * n_psi, 0.0);
-            dep[d].assign(n_beams, 0.0);
-            // the part of the trajectory window that falls into this block
-            int64_t w0 = std::max(traj_first, lo), w1 = std::min(traj_first + traj_count, lo + n);
-            int64_t wc = std::max<int64_t>(0, w1 - w0), wo = w0 - traj_first;
-            auto off = [&](double* b, size_t row) { return (b && wc > 0) ? b + (size_t)wo * row : nullptr; };
-            memset(&cnts[d], 0, sizeof(torj_counters));
-            rcs[d] = torj_trace(m->ctx[d], mp->p[d], opt, n, p3.data(), d3.data(), weight + lo,
-                                per_ray_fm ? freq_hz + lo : freq_hz, per_ray_fm ? mode + lo : mode, per_ray_fm, s_max, n_psi,
-                                psi_edges, n_beams, (n_beams > 1) ? beam_id + lo : nullptr, prof[d].data(), dep[d].data(),
-                                P_final ? P_final + lo : nullptr, P_dep ? P_dep + lo : nullptr, n_points ? n_points + lo : nullptr,
-                                status ? status + lo : nullptr, wc > 0 ? w0 - lo : 0, wc, traj_max_pts,
-                                off(traj_s, traj_max_pts), off(traj_xyz, 3 * (size_t)traj_max_pts), off(traj_P, traj_max_pts),
-                                off(traj_dP_ds, traj_max_pts), off(traj_dP_dV_ray, n_psi), &cnts[d]);
-            if (rcs[d]) errs[d] = g_err;  // g_err is thread-local
-        });
-    }
-    for (auto& t : th) t.join();
+        }
+    });
     for (int d = 0; d < used; ++d)
-        if (rcs[d]) { g_err = "device " + std::to_string(d) + ": " + errs[d]; return rcs[d]; }
-    if (dP_dV) for (size_t k = 0; k < (size_t)n_beams * n_psi; ++k) { double s = 0.0; for (int d = 0; d < used; ++d) s += prof[d][k]; dP_dV[k] = s; }
-    if (deposited_power) for (int b = 0; b < n_beams; ++b) { double s = 0.0; for (int d = 0; d < used; ++d) s += dep[d][b]; deposited_power[b] = s; }
+        if (rcs[d]) {
+            // a workspace in an unknown state is not kept
+            for (int q = 0; q < used; ++q)
+                if (m->ctx[q]->ws) { cudaSetDevice(m->ctx[q]->device); torj_bundle_destroy(m->ctx[q]->ws); m->ctx[q]->ws = nullptr; }
+            g_err = "device " + std::to_string(d) + ": " + errs[d];
+            return rcs[d];
+        }
+    m->used_nccl = do_nccl ? 1 : 0;
+    for (int q = 0; q < n_beams; ++q) {
+        for (int j = 0; j < n_psi + 1; ++j) {
+            double sum = 0.0;
+            if (do_nccl) sum = prof[0][q * prow + j];  // every device holds the all-reduced vector; device 0's copy is returned
+            else for (int d = 0; d < used; ++d) sum += prof[d][q * prow + j];  // device order: bit-reproducible
+            if (j < n_psi) { if (dP_dV) dP_dV[(size_t)q * n_psi + j] = sum; }
+            else if (deposited_power) deposited_power[q] = sum;
+        }
+    }
     if (counters) {
         memset(counters, 0, sizeof(torj_counters));
         for (int d = 0; d < used; ++d) {

@@ -427,12 +427,14 @@ struct HarmCoef {  // per-harmonic invariants
 };
 
 // reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M
-template <int M, int K, bool GENERIC>
+// COOP (a warp per ray, warp-uniform arguments): lane L takes nodes L, L+32, ...; butterfly reduction, so every lane
+// returns the same sum.
+template <int M, int K, bool GENERIC, bool COOP = false>
 __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) {
     double sum = 0.0;
     const int n = c_gl.n;
 #pragma unroll 1
-    for (int k = 0; k < n; ++k) {
+    for (int k = COOP ? (int)(threadIdx.x & 31u) : 0; k < n; k += COOP ? 32 : 1) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
         const double ex = exp_fast(fma(c.e1, t, c.e0));
         const double z = c.x_m * sq;
@@ -455,14 +457,18 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
         pf = fma(c.k6 * t, JD, pf);
         sum = fma(c_gl.w[k] * pf, ex, sum);
     }
+    if (COOP) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    }
     return sum * c.scale;
 }
 
 // rarely taken variants kept out of line so the hot code stays small (instruction cache)
-template <int M>
+template <int M, bool COOP = false>
 __device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M) {  // by value: see eval_field_ext
-    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false>(c, m_rt);
-    return harmonic_sum<(M ? M : 2), 1, true>(c, m_rt);
+    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false, COOP>(c, m_rt);
+    return harmonic_sum<(M ? M : 2), 1, true, COOP>(c, m_rt);
 }
 
 // One harmonic's contribution to alpha [1/m] (sign included), or 0 when a rigorous bound shows it is < floor.
@@ -474,7 +480,7 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M
 #define TORJ_SKIP_MARGIN 1e-10
 #endif
 // M = 0: order given at run time (harmonics above the reference's third; libm jn() throughout).
-template <int M>
+template <int M, bool COOP = false>
 __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe, int m_rt = M) {
     const int m = M ? M : m_rt;
     const double fm = (double)m, ifm = 1.0 / (double)m;
@@ -514,9 +520,9 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     }
     safe = false;
     cnt.n_harm++;
-    if (M == 0 && m > 3) return harmonic_sum<2, 1, true>(c, m);
-    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false>(c, m);
-    return harmonic_sum_large<M>(c, m);
+    if (M == 0 && m > 3) return harmonic_sum<2, 1, true, COOP>(c, m);
+    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false, COOP>(c, m);
+    return harmonic_sum_large<M, COOP>(c, m);
 }
 
 // Harmonics 4..max_harmonic (torj_options.max_harmonic > 3; the reference stops at 3, src/absorption.jl:199). Cold and
@@ -526,12 +532,13 @@ struct HighHarm {
     int n_harm, n_prune;
     bool safe;
 };
+template <bool COOP = false>
 __device__ __noinline__ HighHarm harmonics_above_3(const HarmPre& h, int max_harmonic, double m_0, bool safe) {
     HighHarm r;
     Counters cnt = {};
     r.alpha = 0.0;
     for (int m = 4; m <= max_harmonic; ++m) {
-        if ((double)m >= m_0) r.alpha += harmonic_alpha<0>(h, cnt, safe, m);
+        if ((double)m >= m_0) r.alpha += harmonic_alpha<0, COOP>(h, cnt, safe, m);
         else if (!(m_0 - (double)m > 0.02 * m_0)) safe = false;
     }
     r.n_harm = (int)cnt.n_harm; r.n_prune = (int)cnt.n_prune; r.safe = safe;
@@ -546,7 +553,7 @@ __device__ __noinline__ HighHarm harmonics_above_3(const HarmPre& h, int max_har
 // and m_0 = sqrt(1-N_par^2)/Y to move by 2 % over a distance far below the cell size of the spline tables.
 // HIGH: the instantiation that also sums harmonics 4..max_harmonic (kept out of the default kernels: even an
 // out-of-line call on a never-taken branch cost 6 % there, through the stack copy of HarmPre and its spills).
-template <bool HIGH>
+template <bool HIGH, bool COOP = false>
 __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double iY, double N2, double N_par,
                                               double lnTe, Counters& cnt, bool& skip_ok) {
     skip_ok = false;
@@ -589,15 +596,15 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     double alpha = 0.0;
     bool safe = rc.alpha_floor > 0.0;
     if (rc.max_harmonic >= 2) {
-        if (2.0 >= m_0) alpha += harmonic_alpha<2>(h, cnt, safe);
+        if (2.0 >= m_0) alpha += harmonic_alpha<2, COOP>(h, cnt, safe);
         else if (!(m_0 - 2.0 > 0.02 * m_0)) safe = false;
     }
     if (rc.max_harmonic >= 3) {
-        if (3.0 >= m_0) alpha += harmonic_alpha<3>(h, cnt, safe);
+        if (3.0 >= m_0) alpha += harmonic_alpha<3, COOP>(h, cnt, safe);
         else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
     }
     if (HIGH && rc.max_harmonic >= 4) {
-        const HighHarm r = harmonics_above_3(h, rc.max_harmonic, m_0, safe);
+        const HighHarm r = harmonics_above_3<COOP>(h, rc.max_harmonic, m_0, safe);
         alpha += r.alpha; cnt.n_harm += r.n_harm; cnt.n_prune += r.n_prune; safe = r.safe;
     }
     skip_ok = safe;
@@ -612,12 +619,20 @@ struct PointVals {
     double X, Y, N_par, b[3], Te, Lambda;
 };
 
+// What an absorption model evaluated OUTSIDE rhs<> (the warm-plasma model, torj_warm.cuh) needs from the point
+struct AlphaIn {
+    double X, Y, N2, Np, lnTe, inorm;  // inorm = 1/|dΛ/dN|
+};
+
 // WITH_PSI: du[7] = psi_N at the point and du[8] = grad(psi_N) . dx/ds (inputs of the streaming deposition)
 // alpha_skip (in/out, optional): on entry true = take alpha = 0 without evaluating it (see abs_albajar); on exit, when
 // alpha was evaluated, whether the next step's inner stages may skip it.
-template <bool WITH_ALPHA, bool WITH_PSI = false, bool HIGH = false>
+// COOP: the call is made by a full warp on ONE ray (warp-uniform arguments); the harmonic integrals are split over lanes.
+// ain (optional): filled for an absorption model the caller evaluates itself (then WITH_ALPHA = false, du[6] = 0).
+template <bool WITH_ALPHA, bool WITH_PSI = false, bool HIGH = false, bool COOP = false>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
-                                    PointVals* pv = nullptr, bool skip_alpha = false, bool* skip_ok = nullptr) {
+                                    PointVals* pv = nullptr, bool skip_alpha = false, bool* skip_ok = nullptr,
+                                    AlphaIn* ain = nullptr) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
     const double R2 = fma(x, x, y * y);
     const double iR = rsqrt_fast(R2);
@@ -665,13 +680,14 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
             cnt.n_askip++;
         } else {
             bool ok;
-            const double alpha = abs_albajar<HIGH>(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
+            const double alpha = abs_albajar<HIGH, COOP>(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
             du[6] = -u[6] * alpha;
             if (skip_ok) *skip_ok = ok;
         }
     } else {
         du[6] = 0.0;
     }
+    if (ain) { ain->X = X; ain->Y = Y; ain->N2 = N2; ain->Np = Np; ain->lnTe = f.lnTe; ain->inorm = inorm; }
     cnt.n_rhs++;
     if (pv) {
         pv->X = X; pv->Y = Y; pv->N_par = Np; pv->b[0] = bx; pv->b[1] = by; pv->b[2] = bz;

@@ -6,6 +6,7 @@
 //   k_probe, k_rhs : point probes for parity tests; k_dfma : FP64 peak microbenchmark
 #pragma once
 #include "torj_device.cuh"
+#include "torj_warm.cuh"
 
 namespace torj {
 
@@ -156,7 +157,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         double R = sqrt(x0[0] * x0[0] + x0[1] * x0[1]);
         if (!inside_grid(T, R, x0[2])) {
             double t;
-            if (!box_intersection(T, x0, N0, &t)) { B.status[i] = 2; B.P_dep[i] = -1.0; return; }
+            if (!box_intersection(T, x0, N0, &t)) { B.status[i] = 2; B.n_points[i] = -1; return; }
             for (int k = 0; k < 3; ++k) p[k] = x0[k] + N0[k] * t;
         }
     }
@@ -170,7 +171,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         if (ga == 0.0) root = a;
         else if (gb == 0.0) root = b;
         else {
-            if ((ga < 0.0) == (gb < 0.0)) { B.status[i] = 2; B.P_dep[i] = -2.0; return; }
+            if ((ga < 0.0) == (gb < 0.0)) { B.status[i] = 2; B.n_points[i] = -2; return; }
             for (int it = 0; it < 200; ++it) {
                 double m = 0.5 * (a + b);
                 if (m <= a || m >= b) break;
@@ -182,10 +183,10 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         }
         for (int k = 0; k < 3; ++k) p[k] += root * N0[k];
         double psi_ref = psi_at(T, p);
-        if (!(fabs(psi_ref - T.psi_prof_max) < 1e-6)) { B.status[i] = 2; B.P_dep[i] = -3.0; return; }
+        if (!(fabs(psi_ref - T.psi_prof_max) < 1e-6)) { B.status[i] = 2; B.n_points[i] = -3; return; }
         if (psi_ref > T.psi_prof_max)
             for (int k = 0; k < 3; ++k) p[k] += 2.0 * (psi_ref - T.psi_prof_max) * N0[k];
-        if (!(psi_at(T, p) <= T.psi_prof_max)) { B.status[i] = 2; B.P_dep[i] = -4.0; return; }
+        if (!(psi_at(T, p) <= T.psi_prof_max)) { B.status[i] = 2; B.n_points[i] = -4; return; }
     }
     // ---- vacuum_plasma_refraction (reference src/solve.jl:51-74)
     double Np[3];
@@ -195,7 +196,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
         PointVals pv;
         rhs<false>(T, rc, u, du, c0, &pv);
         Disp d0 = refractive_index_sq<false>(pv.X, pv.Y, 1.0 / pv.Y, 0.0, rc.moded);
-        if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; B.P_dep[i] = -9.0; return; }
+        if (!(d0.Ns2 > 0.0)) { B.status[i] = 1; B.n_points[i] = -9; return; }
         double N_est = sqrt(d0.Ns2);
         double R = sqrt(p[0] * p[0] + p[1] * p[1]);
         double psi, pR, pZ;
@@ -211,7 +212,7 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
             double F[3], J[3][3];
             refraction_equations(N, pv.X, pv.Y, n0, nv, pv.b, rc.moded, F, J);
             double fn = fmax(fabs(F[0]), fmax(fabs(F[1]), fabs(F[2])));
-            if (!(fn == fn)) { status = 2; B.P_dep[i] = -5.0; break; }
+            if (!(fn == fn)) { status = 2; B.n_points[i] = -5; break; }
             if (fn < 1e-12) {
                 // ftol reached (reference src/solve.jl:72). The reference then asserts |Λ| < 1e-12 (src/solve.jl:141), and
                 // |Λ| = |sum_k F_k| can be up to 3 ftol: keep iterating until that assertion holds too instead of
@@ -231,16 +232,16 @@ __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
                 if (f2t == f2t && f2t < f2) { for (int k = 0; k < 3; ++k) N[k] = Nt[k]; stepped = true; break; }
                 lam *= 0.5;
             }
-            if (!stepped) { status = 2; B.P_dep[i] = -6.0 - 1e-3 * it - fn; break; }
+            if (!stepped) { status = 2; B.n_points[i] = -6; break; }
         }
-        if (!ok && status == 0) { status = 2; B.P_dep[i] = -7.0; }
+        if (!ok && status == 0) { status = 2; B.n_points[i] = -7; }
         if (status != 0) { B.status[i] = status; return; }
         for (int k = 0; k < 3; ++k) Np[k] = N[k];
         // assert |Λ| < 1e-12 (reference src/solve.jl:141)
         double u2[7] = {p[0], p[1], p[2], Np[0], Np[1], Np[2], 1.0};
         rhs<false>(T, rc, u2, du, c0, &pv);
         // Λ as the reference forms it: norm(N)^2 - Ns^2
-        if (!(fabs(pv.Lambda) < 1e-12)) { B.status[i] = 2; B.P_dep[i] = -8.0 - fabs(pv.Lambda); return; }
+        if (!(fabs(pv.Lambda) < 1e-12)) { B.status[i] = 2; B.n_points[i] = -8; return; }
     }
     B.u0[i] = p[0]; B.u0[n + i] = p[1]; B.u0[2 * n + i] = p[2];
     B.u0[3 * n + i] = Np[0]; B.u0[4 * n + i] = Np[1]; B.u0[5 * n + i] = Np[2];
@@ -271,6 +272,8 @@ struct TraceArgs {
     double* hand;                     // [n][TORJ_HAND_D] ray state between two segments
     int* seg_done;                    // [n] segments completed; TORJ_SEG_RETIRED once the ray has ended
     int* rays_left;                   // rays not yet retired
+    const double2* warm_tab;          // [501] (t_i, exp(-t_i^2) dt): set_extv! tables of the warm-plasma model
+    double* u_final;                  // [7][n] state of every ray at retirement, or NULL
 };
 #define TORJ_HAND_D 20
 #define TORJ_SEG_RETIRED 0x7fffffff
@@ -309,8 +312,8 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
-// per-ray status codes of include/torj_cuda.h: everything but OK(0) and TRAJ_TRUNCATED(6) ends the ray
-#define TORJ_FATAL(s) ((s) != 0 && (s) != 6)
+// per-ray status codes of include/torj_cuda.h: everything but OK(0), LEFT_GRID(3) and TRAJ_TRUNCATED(6) ends the ray
+#define TORJ_FATAL(s) ((s) != 0 && (s) != 6 && (s) != 3)
 
 // Integrator phases. Every trip of the kernel's main loop evaluates the RHS exactly once per lane that holds a
 // ray, whatever that lane's phase, so the expensive code is always warp-converged; the cheap phase-specific
@@ -327,7 +330,14 @@ enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT 
 #endif
 
 // HIGH = true: harmonics above the third enabled (torj_options.max_harmonic > 3); see abs_albajar
-template <int SCH, bool HIGH = false>
+// MODEL: 0 = Albajar absorption (reference src/absorption.jl), 1 = warm-plasma damping (src/general_absorption.jl α,
+//   torj_warm.cuh): the RHS leaves alpha out and the warp evaluates it cooperatively right after.
+// COOP = true: a WARP per ray instead of a thread per ray (torj_options.lanes_per_ray = 32). All 32 lanes carry the same
+//   ray state and run the same bookkeeping (no divergence, nothing to broadcast); the parallel parts — the nodes of the
+//   harmonic integrals / of the warm quadrature — are split over the lanes and butterfly-reduced, so every lane sees
+//   bit-identical sums. Lane 0 alone performs the side effects (bins, per-ray outputs, queue bookkeeping). For bundles
+//   far below the resident lanes (37 888) and for the warm model, whose alpha costs ~100x the rest of the RHS.
+template <int SCH, bool HIGH = false, int MODEL = 0, bool COOP = false>
 __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
@@ -357,10 +367,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     const long long n = a.B.n_rays;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
+    const bool writer = !COOP || lane == 0;  // the lane that performs a ray's side effects
     const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
-    // q = EEst^beta1 / qold^beta2 / gamma <= 1  <=>  EEst^7 <= gamma^(10 k) qold^4   (beta1 = 7/(10k), beta2 = 4/(10k))
-    const double gamma_pow = pow(gamma_c, 10.0 * ORDER);
+    // OrdinaryDiffEq's step_accept_controller! holds the step (q := 1) when qsteady_min = 1 <= q <= qsteady_max = 1.2.
+    // q = EEst^beta1 / qold^beta2 / gamma <= 1.2  <=>  EEst^7 <= (1.2 gamma)^(10 k) qold^4   (beta1 = 7/(10k), beta2 = 4/(10k))
+    const double qsteady_min = 1.0, qsteady_max = 1.2;
+    const double gamma_pow = pow(qsteady_max * gamma_c, 10.0 * ORDER);
     const double dtmax_pow = pow(O.dtmax, -(double)ORDER);
     const double s_step = O.s_max / (double)O.n_segments;
 
@@ -393,6 +406,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     int seg = 0, last_stat = 0;
     unsigned int rays_ok = 0;
 #endif
+    // warm model, one ray per lane: shared-memory slots where a lane's quadrature sums wait for the serial solve
+    double* wstash = smem + a.n_psi + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + (TORJ_PARK ? TORJ_PARK_SLOTS * TORJ_TPB : 0) + threadIdx.x;
     int phase = PH_IDLE, st = 0;
     bool exhausted = false;
     double u[7], tmp[7];
@@ -415,18 +430,21 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
     double* beam_bins = a.bins;  // this ray's beam row (scans: rays of many launchers / frequencies in one bundle)
     auto sink = [&](int shell, double dP) {
+        pdep += dP;
+        if (!writer) return;
         if (a.n_beams > 1) atomicAdd(&beam_bins[shell], wgt * dP);
         else atomicAdd(&s_bins[shell], wgt * dP);
-        pdep += dP;
         if (tj >= 0) atomicAdd(&a.J.prof[tj * n_psi + shell], dP);  // (a ray may change SMs between segments)
     };
     auto put_point = [&](double s, const double* xx, double P, double dP) {
         if (tj >= 0) {
             if (npts < a.J.max_pts) {
+                if (writer) {
                 size_t o = (size_t)tj * a.J.max_pts + npts;
                 a.J.s[o] = s; a.J.P[o] = P; a.J.dP[o] = dP;
                 size_t ox = (size_t)tj * 3 * a.J.max_pts + npts;
                 a.J.xyz[ox] = xx[0]; a.J.xyz[ox + a.J.max_pts] = xx[1]; a.J.xyz[ox + 2 * (size_t)a.J.max_pts] = xx[2];
+                }
             } else if (rstat == 0) {
                 rstat = 6;  // TORJ_RAY_TRAJ_TRUNCATED
             }
@@ -466,6 +484,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     };
     // segment hand-off: the state a ray carries from one segment to the next (L2-coherent accesses: another SM wrote it)
     auto save_ray = [&]() {
+        if (!writer) return;
         double2* h = reinterpret_cast<double2*>(a.hand + (size_t)ray * TORJ_HAND_D);
         __stcg(h + 0, make_double2(u[0], u[1])); __stcg(h + 1, make_double2(u[2], u[3]));
         __stcg(h + 2, make_double2(u[4], u[5])); __stcg(h + 3, make_double2(u[6], KK(0, 0)));
@@ -500,7 +519,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     // try to start the held item (ray idx, segment wseg): possible once the ray's previous segment has been handed in
     auto claim = [&](long long idx, bool aligned) {
         ray = idx;
-        const int d = atomicAdd(&a.seg_done[idx], 0);
+        int d = atomicAdd(&a.seg_done[idx], 0);
+        if (COOP) d = __shfl_sync(FULL, d, 0);  // one observation for the whole warp (another SM may write in between)
         if (d == TORJ_SEG_RETIRED) {
             phase = PH_IDLE; ray = -1;
         } else if (d == wseg && aligned) {
@@ -510,8 +530,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             } else if (a.B.status[idx] == 0) {
                 start_ray(idx);
             } else {  // failed initialisation (k_ray_init): retire at once
-                atomicExch(&a.seg_done[idx], TORJ_SEG_RETIRED);
-                atomicSub(a.rays_left, 1);
+                if (writer) {
+                    atomicExch(&a.seg_done[idx], TORJ_SEG_RETIRED);
+                    atomicSub(a.rays_left, 1);
+                }
                 phase = PH_IDLE; ray = -1;
             }
         } else {
@@ -535,13 +557,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             unsigned long long base = 0;
             int left = 1;
             if ((int)lane == leader) {
-                base = atomicAdd(a.next_ray, (unsigned long long)__popc(need));
+                base = atomicAdd(a.next_ray, COOP ? 1ull : (unsigned long long)__popc(need));
                 if (a.interleave) left = atomicAdd(a.rays_left, 0);
             }
             base = __shfl_sync(FULL, base, leader);
             left = __shfl_sync(FULL, left, leader);
             if (phase == PH_IDLE && !exhausted) {
-                long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                long long idx = (long long)base + (COOP ? 0 : __popc(need & ((1u << lane) - 1u)));
                 if (!a.interleave) {
                     if (idx >= n) {
                         exhausted = true;
@@ -566,10 +588,26 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // alpha is evaluated in full at the FSAL stage (= first stage of the next step) and in the seed / callback /
         // initial-dt phases; the inner stages take alpha = 0 when that evaluation found every harmonic negligible
         // with a 1e10 margin (abs_albajar)
-        if (phase >= PH_SEED) {
+        if (MODEL == 0) {
+            if (phase >= PH_SEED) {
+                const bool inner = (phase == PH_STAGE && st < S - 1);
+                rhs<true, true, HIGH, COOP>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
+                if (!inner) a_skip = a_skip_next;
+            }
+        } else {
+            // warm-plasma model: the RHS without alpha, then the warp-cooperative alpha of every lane that needs one
+            AlphaIn ain;
+            ain.X = 0.1; ain.Y = 0.5; ain.N2 = 1.0; ain.Np = 0.0; ain.lnTe = -1e300; ain.inorm = 1.0;
+            const bool evaluated = phase >= PH_SEED;
             const bool inner = (phase == PH_STAGE && st < S - 1);
-            rhs<true, true, HIGH>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
-            if (!inner) a_skip = a_skip_next;
+            if (evaluated) rhs<false, true, false, false>(T, rc, tmp, out, cnt, nullptr, false, nullptr, &ain);
+            const bool want = evaluated && !(inner && a_skip);
+            if (evaluated && !want) cnt.n_askip++;
+            const double alpha = warm_alpha_warp<COOP>(a.warm_tab, rc, ain, want, wstash, TORJ_TPB, cnt, a_skip_next);
+            if (evaluated) {
+                out[6] = -tmp[6] * alpha;
+                if (!inner) a_skip = a_skip_next;
+            }
         }
 
         // ---- phase bookkeeping
@@ -645,9 +683,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                         cnt.n_acc++;
                         double ttmp = t + dt;
                         if (fabs(ttmp - tstop) < 100.0 * eps_of(fmax(t, tstop))) ttmp = tstop;
-                        // dt/q >= dt whenever q <= 1; at dt == dtmax the proposal is clipped back to dtmax, so the
-                        // two pow() are needed only when the step must shrink or has to grow back. After the last
-                        // step of a segment the proposal is never used (the next segment is a fresh problem).
+                        // dt/q >= dt whenever q <= 1 and q := 1 in the dead band 1 <= q <= 1.2; at dt == dtmax the
+                        // proposal is clipped back to dtmax, so the two pow() are needed only when the step must
+                        // shrink or has to grow back. After the last step of a segment the proposal is never used
+                        // (the next segment is a fresh problem).
                         const double e2 = EEst * EEst, q2 = qold * qold;
                         if (ttmp == tstop || (dt == O.dtmax && e2 * e2 * e2 * EEst <= gamma_pow * (q2 * q2))) {
                             dtnew = dt;
@@ -657,6 +696,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                                 qq = pow_nl(EEst, beta1) / pow_nl(qold, beta2);
                                 qq = fmax(1.0 / qmax, fmin(1.0 / qmin, qq / gamma_c));
                             }
+                            if (qq >= qsteady_min && qq <= qsteady_max) qq = 1.0;  // steady-state dead band
                             dtnew = dt / qq;
                         }
                         qold = fmax(EEst, qoldinit);
@@ -718,24 +758,31 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 // termination tests at the segment end (reference src/solve.jl:174-176) and retirement
                 bool done = TORJ_FATAL(rstat) || seg >= O.n_segments || psi_cur > O.psi_stop || u[6] < O.p_stop;
                 if (done) {
-                    a.B.status[ray] = rstat;
-                    a.B.n_points[ray] = npts;
+                    if (rstat == 0 && !inside_grid(T, sqrt(u[0] * u[0] + u[1] * u[1]), u[2])) rstat = 3;  // TORJ_RAY_LEFT_GRID
                     last_stat = rstat;
-                    if (!TORJ_FATAL(rstat)) {
-                        a.B.P_final[ray] = u[6];
-                        a.B.P_dep[ray] = pdep;
-                        if (a.n_beams > 1) {
-                            atomicAdd(&beam_bins[n_psi], wgt * pdep);
-                            atomicAdd(&beam_bins[n_psi + 1], wgt);
-                        } else {
-                            tot_dep += wgt * pdep;
-                            tot_w += wgt;
+                    if (writer) {
+                        a.B.status[ray] = rstat;
+                        a.B.n_points[ray] = npts;
+                        if (a.u_final) {
+#pragma unroll
+                            for (int i = 0; i < 7; ++i) a.u_final[(size_t)i * n + ray] = u[i];
                         }
-                        rays_ok++;
-                    }
-                    if (a.interleave) {
-                        atomicExch(&a.seg_done[ray], TORJ_SEG_RETIRED);
-                        atomicSub(a.rays_left, 1);
+                        if (!TORJ_FATAL(rstat)) {
+                            a.B.P_final[ray] = u[6];
+                            a.B.P_dep[ray] = pdep;
+                            if (a.n_beams > 1) {
+                                atomicAdd(&beam_bins[n_psi], wgt * pdep);
+                                atomicAdd(&beam_bins[n_psi + 1], wgt);
+                            } else {
+                                tot_dep += wgt * pdep;
+                                tot_w += wgt;
+                            }
+                            rays_ok++;
+                        }
+                        if (a.interleave) {
+                            atomicExch(&a.seg_done[ray], TORJ_SEG_RETIRED);
+                            atomicSub(a.rays_left, 1);
+                        }
                     }
                     ray = -1;
                     phase = PH_IDLE;
@@ -780,6 +827,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
     // ---- block reduction: warp shuffles, shared-memory atomics, then global atomics
     unsigned long long c6[8] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok, cnt.n_prune, cnt.n_askip};
+    if (!writer) {  // COOP: the other 31 lanes carry copies of lane 0's counts
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c6[q] = 0ull;
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         tot_dep += __shfl_down_sync(FULL, tot_dep, off);
@@ -819,15 +870,26 @@ __global__ void k_finalize(const double* bins, const double* dV, int n_psi, int 
 // probes
 // ------------------------------------------------------------------------------------------------
 // out[11][n]: psi, ne, Te, Bx, By, Bz, X, Y, N_par, Lambda, alpha
+// model: 0 Albajar, 1 warm-plasma (needs 19 * blockDim doubles of dynamic shared memory; whole warps take part)
 __global__ void k_probe(DevTables T, long long n, const double* x, const double* N, double f, int mode, double te_min,
-                        int max_harmonic, double alpha_floor, double* out) {
+                        int max_harmonic, double alpha_floor, int model, const double2* warm_tab, double* out) {
+    extern __shared__ double smem[];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool active = i < n;
+    if (!active) i = n - 1;
     RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double u[7] = {x[i], x[n + i], x[2 * n + i], N[i], N[n + i], N[2 * n + i], 1.0}, du[7];
     Counters c = {0, 0, 0, 0, 0, 0, 0};
     PointVals pv;
-    rhs<true, false, true>(T, rc, u, du, c, &pv);
+    if (model == 1) {
+        AlphaIn ain;
+        bool safe;
+        rhs<false, false, false>(T, rc, u, du, c, &pv, false, nullptr, &ain);
+        du[6] = -u[6] * warm_alpha_warp<false>(warm_tab, rc, ain, active, smem + threadIdx.x, blockDim.x, c, safe);
+    } else {
+        rhs<true, false, true>(T, rc, u, du, c, &pv);
+    }
+    if (!active) return;
     double Babs = pv.Y / rc.cY;
     out[i] = psi_at(T, u);
     out[n + i] = pv.X / rc.cX;
@@ -838,15 +900,64 @@ __global__ void k_probe(DevTables T, long long n, const double* x, const double*
 }
 
 __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int mode, double te_min, int max_harmonic,
-                      double alpha_floor, double* du) {
+                      double alpha_floor, int model, const double2* warm_tab, double* du) {
+    extern __shared__ double smem[];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool active = i < n;
+    if (!active) i = n - 1;
     RayConst rc = make_ray_const(f, mode, te_min, max_harmonic, alpha_floor);
     double uu[7], dd[7];
     for (int q = 0; q < 7; ++q) uu[q] = u[(size_t)q * n + i];
     Counters c = {0, 0, 0, 0, 0, 0, 0};
-    rhs<true, false, true>(T, rc, uu, dd, c);
+    if (model == 1) {
+        AlphaIn ain;
+        bool safe;
+        rhs<false, false, false>(T, rc, uu, dd, c, nullptr, false, nullptr, &ain);
+        dd[6] = -uu[6] * warm_alpha_warp<false>(warm_tab, rc, ain, active, smem + threadIdx.x, blockDim.x, c, safe);
+    } else {
+        rhs<true, false, true>(T, rc, uu, dd, c);
+    }
+    if (!active) return;
     for (int q = 0; q < 7; ++q) du[(size_t)q * n + i] = dd[q];
+}
+
+// α(omega, X, Y, N_r, theta, te, v_g_perp, imod) of reference src/general_absorption.jl:1328-1337 at n points (parity
+// probe). in[7][n]: omega, X, Y, N_r, theta, te, v_g_perp; out[5][n]: N_warm, alpha, lrm, ierr, iterations.
+// One point per lane; the warp does the quadratures one after the other, the owner finishes its own.
+__global__ void k_warm_alpha(long long n, const double* in, int imod, const double2* warm_tab, double* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    const unsigned lane = threadIdx.x & 31u;
+    const double omega = in[i], X = in[n + i], Y = in[2 * n + i], N_r = in[3 * n + i], theta = in[4 * n + i], te = in[5 * n + i],
+                 vg = in[6 * n + i];
+    RayConst rc = make_ray_const(omega / (2.0 * M_PI), imod, 0.0, 3, 0.0);
+    rc.w_over_c = omega / TORJ_C;
+    AlphaIn ain;
+    ain.X = X; ain.Y = Y; ain.N2 = N_r * N_r; ain.Np = N_r * cos(theta); ain.lnTe = log(te); ain.inorm = vg;
+    rc.ln_te_min = -1e300;
+    WarmPrep wp;
+    wp.yg = 0.5; wp.anpl = 0.0; wp.amu = 100.0; wp.anprc = 1.0; wp.sinth = 1.0; wp.lrm = 1;
+    double alpha = 0.0, N_warm = 0.0;
+    int ierr = 0, iters = 0;
+    bool gated, safe;
+    bool needq = active && warm_prepare(rc, ain, wp, alpha, gated, safe);
+    if (active && !needq && wp.lrm < 1) ierr = 98;
+    const int llm = wp.lrm < 3 ? wp.lrm : 3;
+    unsigned m = __ballot_sync(0xffffffffu, needq);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const double yg = __shfl_sync(0xffffffffu, wp.yg, src), anpl = __shfl_sync(0xffffffffu, wp.anpl, src);
+        const double amu = __shfl_sync(0xffffffffu, wp.amu, src);
+        const int l3 = __shfl_sync(0xffffffffu, llm, src);
+        double H[TORJ_WARM_H];
+        warm_hermitian_warp(warm_tab, yg, anpl, amu, l3, H);
+        if ((int)lane == src) alpha = warm_alpha_finish(rc, ain, wp, H, &N_warm, &ierr, &iters);
+    }
+    if (!active) return;
+    out[i] = N_warm; out[n + i] = alpha; out[2 * n + i] = (double)wp.lrm; out[3 * n + i] = (double)ierr;
+    out[4 * n + i] = (double)iters;
 }
 
 // FP64 peak: 8 independent DFMA chains per thread, register resident

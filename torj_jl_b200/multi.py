@@ -1,6 +1,7 @@
-"""Single-process multi-GPU front end (torj_multi_*): one call shards a bundle by contiguous ray blocks over all
-visible GPUs and sums the profiles on the host in device order.  This is what a Julia `make_beam` on a multi-GPU box
-binds; bench.py uses the one-process-per-GPU / NCCL route instead."""
+"""Single-process multi-GPU front end (torj_multi_*): one call shards a bundle over all visible GPUs (contiguous ray
+blocks or beams dealt round-robin) and sums the profiles with one ncclAllReduce over NVLink on the devices' buffers
+(or on the host in device order: `deterministic=True`).  This is what a Julia `make_beam` on a multi-GPU box binds;
+`bench.py --impl multi` times it, the default bench uses the one-process-per-GPU route."""
 from __future__ import annotations
 
 import ctypes as C
@@ -22,6 +23,16 @@ class MultiGPU:
         _lib.check(_lib.lib().torj_multi_create(int(n_devices), C.byref(self.h)))
         self.n_devices = int(_lib.lib().torj_multi_device_count(self.h))
         self._plasmas = {}
+
+    def configure(self, sharding="contiguous", block_rays=1, deterministic=False):
+        """sharding: "contiguous" | "block_cyclic" (blocks of block_rays consecutive rays — one beam — dealt round-robin);
+        deterministic: host sum in device order instead of the NCCL all-reduce."""
+        code = {"contiguous": 0, "block_cyclic": 1}[sharding]
+        _lib.check(_lib.lib().torj_multi_configure(self.h, code, int(block_rays), int(bool(deterministic))))
+
+    @property
+    def used_nccl(self) -> bool:
+        return bool(_lib.lib().torj_multi_used_nccl(self.h))
 
     def abs_Al_init(self, N_absz: int):
         t, w = np.polynomial.legendre.leggauss(int(N_absz))
@@ -47,28 +58,17 @@ class MultiGPU:
     def trace_bundle(self, plasma, ray_positions, ray_directions, ray_weights, f, mode, s_max, psi_dP_dV, *, options=None,
                      beam_id=None, n_beams=1):
         """Same arguments and result keys as torj_jl_b200.trace_bundle (without trajectories)."""
+        from .solve import bundle_result, marshal_bundle
         L = _lib.lib()
-        pos = np.ascontiguousarray(np.asarray(ray_positions, dtype=np.float64).T)
-        dr = np.ascontiguousarray(np.asarray(ray_directions, dtype=np.float64).T)
-        n = pos.shape[1]
-        wt = np.ascontiguousarray(ray_weights, dtype=np.float64)
-        per_ray = int(np.ndim(f) > 0)
-        fr = np.ascontiguousarray(np.atleast_1d(f), dtype=np.float64)
-        md = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mode), fr.shape), dtype=np.int32)
-        psi = np.ascontiguousarray(psi_dP_dV, dtype=np.float64)
+        m = marshal_bundle(ray_positions, ray_directions, ray_weights, f, mode, psi_dP_dV, beam_id, n_beams)
+        o, psi = m["out"], m["psi"]
         opt = options or _lib.default_options()
-        n_beams = int(n_beams) if beam_id is not None else 1
-        bid = np.ascontiguousarray(beam_id, dtype=np.int32) if beam_id is not None else None
-        prof = np.zeros((n_beams, len(psi))); dep = np.zeros(n_beams)
-        Pf = np.zeros(n); Pd = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
-        cnt = _lib.TorjCounters()
-        _lib.check(L.torj_multi_trace(self.h, self._plasma(plasma), C.byref(opt), n, _p(pos), _p(dr), _p(wt), _p(fr),
-                                      md.ctypes.data_as(c_ip), per_ray, float(s_max), len(psi), _p(psi), n_beams,
-                                      bid.ctypes.data_as(c_ip) if bid is not None else None, _p(prof), _p(dep), _p(Pf), _p(Pd),
-                                      npts.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip), 0, 0, 0, None, None, None, None, None,
-                                      C.byref(cnt)))
-        return dict(dP_dV=prof if n_beams > 1 else prof[0], deposited_power=dep if n_beams > 1 else float(dep[0]), P_final=Pf,
-                    P_deposited_ray=Pd, n_points=npts, status=st, counters=cnt.as_dict())
+        _lib.check(L.torj_multi_trace(self.h, self._plasma(plasma), C.byref(opt), m["n"], _p(m["pos"]), _p(m["dir"]), _p(m["w"]),
+                                      _p(m["f"]), m["mode"].ctypes.data_as(c_ip), m["per_ray"], float(s_max), len(psi), _p(psi),
+                                      m["n_beams"], m["beam"].ctypes.data_as(c_ip) if m["beam"] is not None else None,
+                                      _p(o["prof"]), _p(o["dep"]), _p(o["Pf"]), _p(o["Pd"]), o["npts"].ctypes.data_as(c_ip),
+                                      o["st"].ctypes.data_as(c_ip), 0, 0, 0, None, None, None, None, None, C.byref(o["cnt"])))
+        return bundle_result(m)
 
     def close(self):
         if self.h:

@@ -72,17 +72,23 @@ class Plasma:
         nR, nZ = len(self.R_coords), len(self.Z_coords)
         if psi_norm_data.shape != (nR, nZ):
             raise ValueError(f"psi_norm_data must be [nR={nR}, nZ={nZ}]")
-        self.coefs = {"psi": _prefilter_2d(psi_norm_data)}
-        self.coefs["lnne"] = self._make_2d_prof_spline(f8(psi_prof), f8(ne_prof), psi_norm_data)
-        self.coefs["lnTe"] = self._make_2d_prof_spline(f8(psi_prof), f8(Te_prof), psi_norm_data)
-        self.coefs["BR"] = _prefilter_2d(f8(Br_data))
-        self.coefs["BZ"] = _prefilter_2d(f8(Bz_data))
-        self.coefs["Bphi"] = _prefilter_2d(f8(Bphi_data))
+        self._coefs = None  # the six host prefilters run on first use only: build="device" never needs them
         pr, vol = _resample_uniform(f8(eqt1d_psi_norm), f8(eqt1d_volume))  # src/plasma.jl:42-44
         self.vol_coef = _prefilter_1d(vol)
         self.vol_psi0, self.vol_dpsi, self.n_vol = float(pr[0]), float((pr[-1] - pr[0]) / (len(pr) - 1)), len(pr)
         self.psi_prof_max = float(np.max(psi_prof))  # src/plasma.jl:57
         self._handles = {}
+
+    @property
+    def coefs(self):
+        """The six (nR+2)x(nZ+2) coefficient tables of src/plasma.jl:36-41, prefiltered on the host (lazily)."""
+        if self._coefs is None:
+            r = self._raw
+            self._coefs = {"psi": _prefilter_2d(r["psi"]),
+                           "lnne": self._make_2d_prof_spline(r["psi_prof"], r["ne"], r["psi"]),
+                           "lnTe": self._make_2d_prof_spline(r["psi_prof"], r["Te"], r["psi"]),
+                           "BR": _prefilter_2d(r["BR"]), "BZ": _prefilter_2d(r["BZ"]), "Bphi": _prefilter_2d(r["Bphi"])}
+        return self._coefs
 
     @staticmethod
     def _make_2d_prof_spline(psi, prof, psi_norm_data):

@@ -14,7 +14,8 @@ from .synthetic import pol_tor_angles_2_vector
 STATUS_TEXT = {
     1: "cut-off at the vacuum/plasma boundary (reference src/solve.jl:55-59)",
     2: "ray initialisation failed (assertions at reference src/solve.jl:32,138,141)",
-    3: "ray left the grid", 4: "step limit reached", 5: "NaN in the ray state",
+    3: "ray ended outside the (R,Z) grid (informational: traced and deposited as the reference does)",
+    4: "step limit reached", 5: "NaN in the ray state",
     6: "trajectory buffer too small",
 }
 
@@ -23,12 +24,9 @@ def _p(a):
     return a.ctypes.data_as(c_dp)
 
 
-def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, mode, s_max, psi_dP_dV, *,
-                 options=None, ctx=None, trajectories=None, traj_max_pts=None, beam_id=None, n_beams=1):
-    """One torj_trace call on host buffers. trajectories: None or (first, count).
-    beam_id/n_beams: rays of several beams in one bundle -> dP_dV[n_beams, n_psi], deposited_power[n_beams]."""
-    ctx = ctx or _lib.context()
-    L = _lib.lib()
+def marshal_bundle(ray_positions, ray_directions, ray_weights, f, mode, psi_dP_dV, beam_id, n_beams):
+    """The host buffers torj_trace / torj_multi_trace take: component-major [3][n] rays (a Julia Matrix[n,3] as is),
+    per-ray or scalar frequency / mode, psi levels, beam ids, and the result arrays."""
     pos = np.ascontiguousarray(np.asarray(ray_positions, dtype=np.float64).T)
     dr = np.ascontiguousarray(np.asarray(ray_directions, dtype=np.float64).T)
     n = pos.shape[1]
@@ -37,27 +35,51 @@ def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, 
     fr = np.ascontiguousarray(np.atleast_1d(f), dtype=np.float64)
     md = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mode), fr.shape), dtype=np.int32)
     psi = np.ascontiguousarray(psi_dP_dV, dtype=np.float64)
-    opt = options or _lib.default_options()
     n_beams = int(n_beams) if beam_id is not None else 1
     bid = np.ascontiguousarray(beam_id, dtype=np.int32) if beam_id is not None else None
     if bid is not None and bid.shape != (n,):
         raise ValueError("beam_id must have one entry per ray")
-    prof = np.zeros((n_beams, len(psi))); dep = np.zeros(n_beams)
-    Pf = np.zeros(n); Pd = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32)
-    cnt = _lib.TorjCounters()
+    out = dict(prof=np.zeros((n_beams, len(psi))), dep=np.zeros(n_beams), Pf=np.zeros(n), Pd=np.zeros(n),
+               npts=np.zeros(n, dtype=np.int32), st=np.zeros(n, dtype=np.int32), cnt=_lib.TorjCounters())
+    return dict(pos=pos, dir=dr, n=n, w=wt, per_ray=per_ray, f=fr, mode=md, psi=psi, n_beams=n_beams, beam=bid, out=out)
+
+
+def bundle_result(m):
+    o, nb = m["out"], m["n_beams"]
+    return dict(dP_dV=o["prof"] if nb > 1 else o["prof"][0], deposited_power=o["dep"] if nb > 1 else float(o["dep"][0]),
+                P_final=o["Pf"], P_deposited_ray=o["Pd"], n_points=o["npts"], status=o["st"], counters=o["cnt"].as_dict())
+
+
+def trace_bundle(plasma: Plasma, ray_positions, ray_directions, ray_weights, f, mode, s_max, psi_dP_dV, *,
+                 options=None, ctx=None, trajectories=None, traj_max_pts=None, beam_id=None, n_beams=1):
+    """One torj_trace call on host buffers. trajectories: None or (first, count).
+    beam_id/n_beams: rays of several beams in one bundle -> dP_dV[n_beams, n_psi], deposited_power[n_beams]."""
+    ctx = ctx or _lib.context()
+    L = _lib.lib()
+    m = marshal_bundle(ray_positions, ray_directions, ray_weights, f, mode, psi_dP_dV, beam_id, n_beams)
+    n, psi, o = m["n"], m["psi"], m["out"]
+    opt = options or _lib.default_options()
     t_first, t_count = trajectories if trajectories else (0, 0)
     if t_count and traj_max_pts is None:
         traj_max_pts = 2 + int(opt.n_segments * (np.ceil(s_max / opt.n_segments / opt.dtmax) + 8))
     tm = int(traj_max_pts or 0)
     ts = np.zeros((t_count, tm)); txyz = np.zeros((t_count, 3, tm)); tP = np.zeros((t_count, tm))
     tdP = np.zeros((t_count, tm)); tprof = np.zeros((t_count, len(psi)))
-    _lib.check(L.torj_trace(ctx, plasma.handle(ctx), C.byref(opt), n, _p(pos), _p(dr), _p(wt), _p(fr),
-                            md.ctypes.data_as(c_ip), per_ray, float(s_max), len(psi), _p(psi), n_beams,
-                            bid.ctypes.data_as(c_ip) if bid is not None else None, _p(prof), _p(dep),
-                            _p(Pf), _p(Pd), npts.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip), t_first, t_count, tm,
-                            _p(ts), _p(txyz), _p(tP), _p(tdP), _p(tprof), C.byref(cnt)))
-    return dict(dP_dV=prof if n_beams > 1 else prof[0], deposited_power=dep if n_beams > 1 else float(dep[0]), P_final=Pf, P_deposited_ray=Pd, n_points=npts, status=st,
-                counters=cnt.as_dict(), traj_s=ts, traj_xyz=txyz, traj_P=tP, traj_dP_ds=tdP, traj_dP_dV_ray=tprof)
+    _lib.check(L.torj_trace(ctx, plasma.handle(ctx), C.byref(opt), n, _p(m["pos"]), _p(m["dir"]), _p(m["w"]), _p(m["f"]),
+                            m["mode"].ctypes.data_as(c_ip), m["per_ray"], float(s_max), len(psi), _p(psi), m["n_beams"],
+                            m["beam"].ctypes.data_as(c_ip) if m["beam"] is not None else None, _p(o["prof"]), _p(o["dep"]),
+                            _p(o["Pf"]), _p(o["Pd"]), o["npts"].ctypes.data_as(c_ip), o["st"].ctypes.data_as(c_ip), t_first,
+                            t_count, tm, _p(ts), _p(txyz), _p(tP), _p(tdP), _p(tprof), C.byref(o["cnt"])))
+    res = bundle_result(m)
+    res.update(traj_s=ts, traj_xyz=txyz, traj_P=tP, traj_dP_ds=tdP, traj_dP_dV_ray=tprof)
+    return res
+
+
+def cylindrical_state(xyz, P):
+    """R, phi, tau = -ln P of Cartesian samples (the reference's state is Cartesian, src/solve.jl:144); xyz [..., 3, n]."""
+    x, y = xyz[..., 0, :], xyz[..., 1, :]
+    with np.errstate(divide="ignore"):
+        return np.hypot(x, y), np.arctan2(y, x), -np.log(P)
 
 
 def make_ray(plasma: Plasma, x0, N_vacuum, f, mode, s_max, psi_dP_dV, *, options=None, ctx=None):
@@ -66,7 +88,7 @@ def make_ray(plasma: Plasma, x0, N_vacuum, f, mode, s_max, psi_dP_dV, *, options
     r = trace_bundle(plasma, np.asarray(x0, dtype=np.float64)[None, :], np.asarray(N_vacuum, dtype=np.float64)[None, :],
                      [1.0], float(f), int(mode), s_max, psi_dP_dV, options=options, ctx=ctx, trajectories=(0, 1))
     st = int(r["status"][0])
-    if st not in (0,):
+    if st not in (0, 3):
         # the reference raises AssertionError / MethodError at src/solve.jl:32,138,141
         raise AssertionError(STATUS_TEXT.get(st, f"ray status {st}"))
     n = int(r["n_points"][0])
@@ -85,7 +107,7 @@ def make_beam(plasma: Plasma, r, phi, z, steering_angle_tor, steering_angle_pol,
     n = len(wts)
     res = trace_bundle(plasma, pos, dirs, wts, float(f), int(mode), s_max, psi_dP_dV, options=options, ctx=ctx,
                        trajectories=(0, n))
-    bad = np.nonzero(~np.isin(res["status"], (0,)))[0]
+    bad = np.nonzero(~np.isin(res["status"], (0, 3)))[0]
     if len(bad):
         raise AssertionError(f"ray {int(bad[0])}: " + STATUS_TEXT.get(int(res['status'][bad[0]]), "failed"))
     arc, traj, powers = [], [], []
