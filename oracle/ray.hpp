@@ -66,8 +66,9 @@ struct RayResult {
 // ---------------------------------------------------------------------------------------------
 // RHS: reference src/solve.jl:85-95
 // ---------------------------------------------------------------------------------------------
+// skip_alpha / safe: the inner-stage rule of the CUDA path (only ever set when rp.alpha_floor > 0, i.e. for timing)
 inline void grad_lambda(const Plasma& pl, const AbsQuad& q, const RayParams& rp, const double u[7], double du[7],
-                        RayCounters* cnt) {
+                        RayCounters* cnt, bool skip_alpha = false, bool* safe = nullptr) {
     typedef Dual<3> D;
     D xd[3] = {D::seed(u[0], 0), D::seed(u[1], 1), D::seed(u[2], 2)};
     D Nc[3] = {D(u[3]), D(u[4]), D(u[5])};
@@ -80,8 +81,9 @@ inline void grad_lambda(const Plasma& pl, const AbsQuad& q, const RayParams& rp,
         du[k] = LN.d[k] / nrm;
         du[3 + k] = -(Lx.d[k] / nrm);
     }
-    if (rp.absorption_model == 1) du[6] = -u[6] * alpha_warm_approx(pl, rp, u, u + 3, 1.0 / nrm, cnt ? &cnt->abs : nullptr);
-    else du[6] = -u[6] * alpha_approx(pl, q, rp, u, u + 3, cnt ? &cnt->abs : nullptr);
+    if (skip_alpha) { du[6] = 0.0; if (cnt) cnt->abs.n_askip++; }
+    else if (rp.absorption_model == 1) du[6] = -u[6] * alpha_warm_approx(pl, rp, u, u + 3, 1.0 / nrm, cnt ? &cnt->abs : nullptr);
+    else du[6] = -u[6] * alpha_approx(pl, q, rp, u, u + 3, cnt ? &cnt->abs : nullptr, safe);
     if (cnt) cnt->n_rhs++;
 }
 
@@ -324,6 +326,7 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
     rp.te_min = opt.te_min;
     rp.max_harmonic = opt.max_harmonic;
     rp.absorption_model = opt.absorption_model;
+    rp.alpha_floor = opt.absorption_model == 0 ? opt.alpha_floor : 0.0;
     const Tableau& tb = opt.scheme == 1 ? tableau_owrenzen3() : tableau_tsit5();
     const int S = tb.stages;
 
@@ -370,7 +373,8 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
         double t = (double)(seg - 1) * s_step + s0;
         const double tstop = (double)seg * s_step + s0;
         // ---- fresh integrator: f0, initial dt (Hairer), controller memory
-        grad_lambda(pl, q, rp, u, k[0], &res.cnt);
+        bool a_skip = false;  // inner stages of the next step may take alpha = 0 (alpha_floor > 0 only)
+        grad_lambda(pl, q, rp, u, k[0], &res.cnt, false, &a_skip);
         double dt;
         {
             double sk[7], a0[7], a1[7];
@@ -384,7 +388,7 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
             } else {
                 double u1[7], f1[7], a2[7];
                 for (int i = 0; i < 7; ++i) u1[i] = u[i] + dt0 * k[0][i];
-                grad_lambda(pl, q, rp, u1, f1, &res.cnt);
+                grad_lambda(pl, q, rp, u1, f1, &res.cnt, false, &a_skip);
                 for (int i = 0; i < 7; ++i) a2[i] = (f1[i] - k[0][i]) / sk[i];
                 double d2 = rms(a2) / dt0;
                 double md = std::max(d1, d2);
@@ -404,7 +408,8 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
                     for (int j = 0; j < st; ++j) acc += tb.a[st][j] * k[j][i];
                     tmp[i] = u[i] + dt * acc;
                 }
-                grad_lambda(pl, q, rp, tmp, k[st], &res.cnt);
+                if (st < S - 1) grad_lambda(pl, q, rp, tmp, k[st], &res.cnt, a_skip && rp.alpha_floor > 0.0, nullptr);
+                else grad_lambda(pl, q, rp, tmp, k[st], &res.cnt, false, &a_skip);  // FSAL stage: full alpha
             }
             for (int i = 0; i < 7; ++i) unew[i] = tmp[i];  // last stage argument is the new state (FSAL)
             double at[7];
@@ -437,7 +442,7 @@ inline void make_ray(const Plasma& pl, const AbsQuad& q, const Options& opt, con
                 for (int i = 0; i < 7; ++i) { u[i] = unew[i]; k[0][i] = k[S - 1][i]; }
                 if (u[6] < 0.0) {  // positivity callback, reference src/solve.jl:78-83,159-160
                     u[6] = 0.0;
-                    grad_lambda(pl, q, rp, u, k[0], &res.cnt);
+                    grad_lambda(pl, q, rp, u, k[0], &res.cnt, false, &a_skip);
                 }
                 // dP/ds sample = P*alpha at the saved state (src/solve.jl:171) = -k[0][6]
                 push(t, u, u[6], -k[0][6], k[0], -k[0][6]);

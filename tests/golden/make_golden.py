@@ -8,6 +8,9 @@ Sources (none of them is the repo's own CUDA path):
   bessel_gl.npz     scipy.special.jv (= SpecialFunctions.besselj), numpy leggauss (= FastGaussQuadrature.gausslegendre)
   oracle_ray.npz    REGRESSION fixture produced by the oracle itself (config-1 stand-in ray, every 50th sample);
                     the Julia reference cannot run here, so this pins the oracle against drift, not against Julia.
+  warm_alpha.npz    REGRESSION fixture of the oracle's restatement of α (reference src/general_absorption.jl:1328-1337)
+                    on a deterministic grid of (X, Y, N, theta, Te, mode); same caveat: drift only, not Julia. The special
+                    functions underneath are pinned against scipy in tests/test_oracle_warm.py.
 """
 import os
 import sys
@@ -70,6 +73,22 @@ def oracle_ray():
              P=r["P"][sl], deposited=r["deposited_power"], P_end=r["P"][-1], dP_dV=r["dP_dV"][::10], counters=r["counters"])
 
 
+def warm_alpha():
+    from oracle import torj_oracle as O
+    rows, outs = [], []
+    for f in (95e9, 110e9, 170e9):
+        for X in (0.05, 0.3):
+            for Y in (0.31, 0.34, 0.49, 0.505, 0.52, 0.98, 1.03):
+                for th in (np.pi / 2 - 1e-3, 1.35, 1.1, 2.0):
+                    for te in (800.0, 5e3, 25e3):
+                        for imod in (1, -1):
+                            row = [2 * np.pi * f, X, Y, 0.9 - 0.3 * X, th, te, 0.55, imod]
+                            o = O.warm_alpha(*row[:7], imod)
+                            rows.append(row)
+                            outs.append([o["N_warm"], o["alpha"], o["lrm"], o["ierr"], o["iterations"]])
+    np.savez(os.path.join(OUT, "warm_alpha.npz"), inputs=np.array(rows), outputs=np.array(outs))
+
+
 if __name__ == "__main__":
-    fitpack_case(); launch_known(); bessel_gl(); oracle_ray()
+    fitpack_case(); launch_known(); bessel_gl(); oracle_ray(); warm_alpha()
     print("golden fixtures written to", OUT)

@@ -146,7 +146,8 @@ def test_init_failure_statuses_do_not_abort_the_batch(gpu_small, arrays_small, l
     dirs = np.array([launcher["N0"], -launcher["N0"], launcher["N0"]])
     res = tj.trace_bundle(gpu_small, pos, dirs, [0.5, 0.25, 0.25], launcher["f"], 1, 0.3, np.linspace(0, 1, 64))
     assert list(res["status"]) == [0, 2, 0]                 # second ray points away: no bracket (src/solve.jl:29)
-    assert res["counters"]["n_rays_ok"] == 2 and res["P_final"][1] == 0.0 and res["n_points"][1] == 0
+    assert res["counters"]["n_rays_ok"] == 2 and res["P_final"][1] == 0.0 and res["P_deposited_ray"][1] == 0.0
+    assert res["n_points"][1] == -2                         # diagnostic of the failing check, never a power (include/torj_cuda.h)
     assert abs(res["P_final"][0] - res["P_final"][2]) < 1e-9   # off-grid launcher enters through the box (src/solve.jl:22-25)
     dense = dict(arrays_small); dense["ne_prof"] = np.full_like(dense["ne_prof"], 1e20)
     r2 = tj.trace_bundle(tj.Plasma(*dense.values()), pos[:1], dirs[:1], [1.0], 60e9, 1, 0.3, np.linspace(0, 1, 64))

@@ -1,0 +1,413 @@
+"""Round-2 parity tests of the CUDA path (through the C ABI) against the CPU oracle:
+warm-plasma absorption model, a warp per ray (lanes_per_ray = 32), step-size dead band, derived
+outputs, informational statuses, the multi-GPU front end's collective, and wider full-size checks of configs 3 and 4.
+
+Tolerances as in test_gpu_parity.py (trajectories 1e-9 m, absorbed fraction 1e-6 relative, profile L2 1e-4 against the
+reference's spline-root deposition, 1e-9 like for like). For the warm model alpha itself is compared at
+|d alpha| <= 1e-9 |alpha| + 1e-12 1/m: alpha = 2 Im(N_perp^2) w/c v_g, and the rounding of the complex arithmetic is
+relative to |N_perp^2|, not to its imaginary part (2 w/c 1e-16 ~ 1e-12 1/m).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy import interpolate
+
+import torj_jl_b200 as tj
+from conftest import GOLDEN
+from oracle import torj_oracle as O
+from torj_jl_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+PSI = np.linspace(0.0, 1.0, 1000)
+TRAJ_TOL, FRAC_TOL, L2_FAITHFUL, L2_LIKE = 1e-9, 1e-6, 1e-4, 1e-9
+
+
+def l2rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _abs_al_init():
+    tj.abs_Al_init(24)
+
+
+@pytest.fixture(scope="module")
+def gpu_full(arrays_full):
+    return tj.Plasma(*arrays_full.values())
+
+
+@pytest.fixture(scope="module")
+def gpu_small(arrays_small):
+    return tj.Plasma(*arrays_small.values())
+
+
+def hot_arrays(n, te0):
+    """SURVEY.md §8(d) config 5 equilibrium: the Solov'ev case with T_e0 = 10 / 15 / 25 keV."""
+    arr = tj.solovev_arrays(n, n)
+    psi = arr["psi_prof"]
+    arr["Te_prof"] = te0 * (1.0 - psi) ** 2 + 50.0
+    return arr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# warm-plasma model: alpha, RHS, rays, beams
+# ------------------------------------------------------------------------------------------------------------------
+def test_warm_alpha_scan_against_oracle():
+    """torj_warm_alpha == α(omega, X, Y, N_r, theta, te, v_g_perp, imod) of reference src/general_absorption.jl:1328-1337 as the
+    oracle restates it, on the 1008-point grid of tests/golden/warm_alpha.npz (3 frequencies x X x Y around the first three
+    harmonics x angle x T_e up to 25 keV x both modes)."""
+    g = np.load(GOLDEN + "/warm_alpha.npz")
+    inp, ref = g["inputs"], g["outputs"]
+    worst, n_cmp = 0.0, 0
+    for imod in (1, -1):
+        sel = inp[:, 7] == imod
+        a = inp[sel]
+        Nw, al = tj.warm_alpha(a[:, 0], a[:, 1], a[:, 2], a[:, 3], a[:, 4], a[:, 5], a[:, 6], imod)
+        r = ref[sel]
+        assert np.array_equal(tj.warm_alpha.last["lrm"], r[:, 2].astype(int))
+        conv = r[:, 4] < 100                        # the fixed-point iteration converged (errnpr < 1e-4 within imx = 100)
+        assert np.array_equal(tj.warm_alpha.last["ierr"][conv], r[conv, 3].astype(int))
+        d = np.abs(al[conv] - r[conv, 1])
+        tol = 1e-9 * np.abs(r[conv, 1]) + 1e-12
+        worst = max(worst, float(np.max(d / tol)))
+        n_cmp += int(conv.sum())
+        # an iteration count one off (errnpr crossing 1e-4 within rounding) moves N_perp^2 by < 1e-4 of a contraction step
+        assert np.mean(d <= tol) > 0.98, np.sort(d / tol)[-10:]
+        assert np.all(d <= 1e-5 * np.abs(r[conv, 1]) + 1e-10)
+        assert np.max(np.abs(Nw[conv] - r[conv, 0]) / np.abs(r[conv, 0])) < 1e-6
+    print(f"warm alpha: {n_cmp} converged points compared, worst |d alpha| / (1e-9 |alpha| + 1e-12) = {worst:.3g}")
+
+
+def test_warm_rhs_and_probe_match_oracle(gl24, launcher):
+    arr = hot_arrays(129, 10e3)
+    pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
+    warm = tj.default_options(absorption_model=1, alpha_floor=0.0)
+    f = 110e9
+    ray = pl_state_along(opl, launcher, f, 24)
+    du = pl.rhs(ray, f, 1, options=warm)
+    for k in range(len(ray)):
+        ref = opl.rhs(ray[k], f, 1, gl24, absorption_model=1)
+        assert np.abs(du[k, :6] - ref[:6]).max() < 1e-10
+        assert abs(du[k, 6] - ref[6]) <= 1e-9 * abs(ref[6]) + 1e-12, (k, du[k, 6], ref[6])
+    pr = pl.probe(ray[:, :3], ray[:, 3:6], f, 1, options=warm)
+    assert np.abs(pr["alpha"] + du[:, 6]).max() <= 1e-12 * np.abs(du[:, 6]).max()
+    assert np.abs(du[:, 6]).max() > 1.0                             # the scan does cross the absorbing layer
+
+
+def pl_state_along(opl, launcher, f, n):
+    """n states (x, N, 1) along the central ray, N on the cold dispersion surface: from the oracle's ray initialisation and a
+    straight march (the RHS comparison needs consistent states, not a trajectory)."""
+    st, init = opl.ray_init(launcher["x0"], launcher["N0"], f, 1)
+    assert st == 0
+    out = []
+    x, N = init[:3].copy(), init[3:6].copy()
+    for k in range(n):
+        out.append(np.concatenate([x + 0.03 * k * N / np.linalg.norm(N), N, [1.0]]))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("lanes", [1, 32])
+def test_warm_single_ray_against_oracle(gl24, launcher, lanes):
+    """One ray of the config-5 equilibrium (T_e0 = 10 keV, 110 GHz) with the warm model: same accepted steps, trajectory,
+    power and deposition as the oracle's make_ray with absorption_model = 1, one thread per ray and a warp per ray."""
+    arr = hot_arrays(129, 10e3)
+    pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
+    psi = np.linspace(0.0, 1.0, 300)
+    opt = tj.default_options(absorption_model=1, alpha_floor=0.0, lanes_per_ray=lanes)
+    s, u, P, prof, dep = tj.make_ray(pl, launcher["x0"], launcher["N0"], 110e9, 1, 0.3, psi, options=opt)
+    ro = opl.make_ray(launcher["x0"], launcher["N0"], 110e9, 1, 0.3, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
+    assert ro["status"] == 0 and len(s) == len(ro["s"])
+    xyz = np.array(u)
+    assert max(np.abs(xyz[:, 0] - ro["x"]).max(), np.abs(xyz[:, 1] - ro["y"]).max(), np.abs(xyz[:, 2] - ro["z"]).max()) < TRAJ_TOL
+    assert np.abs(P - ro["P"]).max() < 1e-8
+    assert 0.05 < ro["deposited_power"]
+    assert abs(dep - ro["deposited_power"]) <= FRAC_TOL * ro["deposited_power"]
+    assert l2rel(prof, ro["dP_dV"]) < L2_FAITHFUL
+
+
+def test_warm_beam_gate_and_mappings_agree(gl24, launcher):
+    """8-ray beam, warm model: the alpha_floor gate of the quadrature is invisible at tolerance, a warp per ray and a thread
+    per ray agree, and the beam's absorbed fraction / profile match the oracle (rel 1e-6 / L2 1e-4)."""
+    arr = hot_arrays(129, 15e3)
+    pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], 170e9,
+                                             N_rings=2, min_azimuthal_points=3)
+    psi = np.linspace(0.0, 1.0, 200)
+    runs = {}
+    for name, kw in dict(exact1=dict(alpha_floor=0.0, lanes_per_ray=1), exact32=dict(alpha_floor=0.0, lanes_per_ray=32),
+                         gated=dict(lanes_per_ray=0)).items():
+        runs[name] = tj.trace_bundle(pl, pos, dirs, w, 170e9, 1, 0.35, psi, options=tj.default_options(absorption_model=1, **kw))
+        assert (runs[name]["status"] == 0).all()
+    a, b, c = runs["exact1"], runs["exact32"], runs["gated"]
+    assert np.array_equal(a["n_points"], b["n_points"]) and np.array_equal(a["n_points"], c["n_points"])
+    assert np.abs(a["P_final"] - b["P_final"]).max() < 1e-9 and np.abs(a["P_final"] - c["P_final"]).max() < 1e-9
+    assert a["counters"]["n_harm"] == b["counters"]["n_harm"] > 0 and a["counters"]["n_harm_pruned"] == 0
+    assert c["counters"]["n_harm"] + c["counters"]["n_harm_pruned"] <= a["counters"]["n_harm"]
+    assert c["counters"]["n_alpha"] + c["counters"]["n_alpha_skipped"] == a["counters"]["n_alpha"] == a["counters"]["n_rhs"]
+    ref = opl.trace_bundle(pos, dirs, w, 170e9, 1, 0.35, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
+    assert np.array_equal(a["n_points"], ref["n_points"])
+    for r in (a, b, c):
+        assert abs(r["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+        assert l2rel(r["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
+    assert ref["deposited_power"] > 0.01
+
+
+def test_warm_model_option_validation(gpu_small, launcher):
+    for kw in (dict(absorption_model=2), dict(lanes_per_ray=8), dict(absorption_model=1, max_harmonic=5)):
+        with pytest.raises(tj.TorjError):
+            tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.1, PSI, options=tj.default_options(**kw))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# a warp per ray with the reference's Albajar model (small bundles)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("schedule", [0, 2])
+def test_warp_per_ray_albajar(gpu_full, oracle_full, gl24, launcher, schedule):
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    one = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(lanes_per_ray=1),
+                          trajectories=(3, 2))
+    wrp = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI,
+                          options=tj.default_options(lanes_per_ray=32, schedule=schedule), trajectories=(3, 2))
+    assert (wrp["status"] == 0).all() and np.array_equal(one["n_points"], wrp["n_points"])
+    assert one["counters"] == wrp["counters"]                      # lane 0 alone counts: no 32-fold totals
+    assert np.abs(one["P_final"] - wrp["P_final"]).max() < 1e-12   # same arithmetic but for the order of the node sums
+    assert np.abs(one["traj_xyz"] - wrp["traj_xyz"]).max() < 1e-12 and np.abs(one["traj_dP_ds"] - wrp["traj_dP_ds"]).max() < 1e-9
+    assert l2rel(wrp["dP_dV"], one["dP_dV"]) < 1e-11
+    ref = oracle_full.trace_bundle(pos, dirs, w, launcher["f"], 1, 1.0, PSI, gl24, also_streaming=True)
+    assert np.array_equal(wrp["n_points"], ref["n_points"])
+    assert abs(wrp["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(wrp["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL and l2rel(wrp["dP_dV"], ref["dP_dV_streaming"]) < L2_LIKE
+
+
+def test_warp_per_ray_high_harmonics_and_exact_mode(gl24, launcher):
+    arr = hot_arrays(65, 10e3)
+    pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], 225e9,
+                                             N_rings=2, min_azimuthal_points=3)
+    psi = np.linspace(0, 1, 100)
+    opt = tj.default_options(lanes_per_ray=32, max_harmonic=5, alpha_floor=0.0)
+    res = tj.trace_bundle(pl, pos, dirs, w, 225e9, 1, 0.5, psi, options=opt)
+    ref = opl.trace_bundle(pos, dirs, w, 225e9, 1, 0.5, psi, gl24, opts=O.OracleOptions.default(max_harmonic=5))
+    assert np.array_equal(res["n_points"], ref["n_points"]) and np.abs(res["P_final"] - ref["P_final"]).max() < 1e-10
+    assert res["counters"]["n_harm"] == int(ref["counters"]["n_harm"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# integrator: steady-state dead band of the PI controller
+# ------------------------------------------------------------------------------------------------------------------
+def test_step_controller_with_rejections_and_dead_band(gpu_full, oracle_full, gl24, launcher):
+    """dtmax = 1 cm makes the run tolerance-limited: steps are rejected and resized, and OrdinaryDiffEq's accept branch holds
+    dt whenever 1 <= q <= 1.2. Same accepted/rejected sequence as the oracle, ray by ray."""
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=2, min_azimuthal_points=3)
+    for scheme in (0, 1):
+        kw = dict(dtmax=1e-2, scheme=scheme, n_segments=20)
+        res = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(**kw), trajectories=(0, 1))
+        ref = oracle_full.trace_bundle(pos, dirs, w, launcher["f"], 1, 1.0, PSI, gl24, opts=O.OracleOptions.default(**kw))
+        assert res["counters"]["n_rej"] == int(ref["counters"]["n_rej"]) > 0
+        assert np.array_equal(res["n_points"], ref["n_points"])
+        assert np.abs(res["P_final"] - ref["P_final"]).max() < 1e-10
+        ray = oracle_full.make_ray(pos[0], dirs[0], launcher["f"], 1, 1.0, PSI, gl24, opts=O.OracleOptions.default(**kw))
+        n = int(res["n_points"][0])
+        ds = np.diff(res["traj_s"][0, 1:n])
+        assert np.abs(res["traj_s"][0, :n] - ray["s"]).max() < 1e-12 and np.abs(res["traj_xyz"][0, 0, :n] - ray["x"]).max() < TRAJ_TOL
+        held = np.sum(np.abs(np.diff(ds)) < 1e-15 * ds[:-1]) / len(ds)
+        assert len(np.unique(np.round(ds, 12))) > 5 and held > 0.3     # the step varies, and is held for stretches
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# derived outputs, statuses, shared quadrature table
+# ------------------------------------------------------------------------------------------------------------------
+def test_final_state_and_cylindrical_outputs(gpu_small, oracle_small, gl24, launcher):
+    L = tj.lib()
+    pos = np.array([launcher["x0"], launcher["x0"], launcher["x0"]])
+    dirs = np.array([launcher["N0"], -launcher["N0"], tj.pol_tor_angles_2_vector(np.deg2rad(25.0), 0.2)])
+    psi = np.linspace(0, 1, 64)
+    ctx = _lib.context()
+    bh = _lib.c_vp()
+    dp = lambda a: a.ctypes.data_as(_lib.c_dp)
+    posT, dirT, w = np.ascontiguousarray(pos.T), np.ascontiguousarray(dirs.T), np.array([0.5, 0.25, 0.25])
+    fr, md = np.array([95e9]), np.array([1], dtype=np.int32)
+    _lib.check(L.torj_bundle_create(ctx, 3, dp(posT), dp(dirT), dp(w), dp(fr), md.ctypes.data_as(_lib.c_ip), 0, C.byref(bh)))
+    try:
+        _lib.check(L.torj_bundle_set_window(bh, 0, 3, 4200))
+        _lib.check(L.torj_bundle_trace(bh, gpu_small.handle(ctx), None, 0.4, len(psi), dp(psi)))
+        u = np.zeros((7, 3)); R = np.zeros(3); phi = np.zeros(3); tau = np.zeros(3)
+        _lib.check(L.torj_bundle_final_state(bh, dp(u), dp(R), dp(phi), dp(tau)))
+        Pf = np.zeros(3); st = np.zeros(3, dtype=np.int32); npts = np.zeros(3, dtype=np.int32)
+        _lib.check(L.torj_bundle_results(bh, None, None, dp(Pf), None, npts.ctypes.data_as(_lib.c_ip), st.ctypes.data_as(_lib.c_ip), None))
+        assert list(st) == [0, 2, 0] and npts[1] == -2 and Pf[1] == 0.0          # no psi bracket: diagnostic, not a power
+        assert np.isnan(u[:, 1]).all() and np.isnan(R[1]) and np.isnan(tau[1])
+        for i in (0, 2):
+            ro = oracle_small.make_ray(pos[i], dirs[i], 95e9, 1, 0.4, psi, gl24)
+            assert np.abs(u[:, i] - ro["u_final"]).max() < 1e-9
+            assert abs(R[i] - np.hypot(ro["x"][-1], ro["y"][-1])) < 1e-9 and abs(phi[i] - np.arctan2(ro["y"][-1], ro["x"][-1])) < 1e-9
+            assert abs(tau[i] + np.log(ro["P"][-1])) < 1e-8 and u[6, i] == Pf[i]
+        tR = np.zeros((3, 4200)); tphi = np.zeros((3, 4200)); ttau = np.zeros((3, 4200))
+        _lib.check(L.torj_bundle_trajectories_cyl(bh, dp(tR), dp(tphi), dp(ttau)))
+        ro = oracle_small.make_ray(pos[2], dirs[2], 95e9, 1, 0.4, psi, gl24)
+        n = int(npts[2])
+        assert np.abs(tR[2, :n] - np.hypot(ro["x"], ro["y"])).max() < 1e-9 and np.abs(ttau[2, :n] + np.log(ro["P"])).max() < 1e-8
+        assert np.abs(tphi[2, :n] - np.arctan2(ro["y"], ro["x"])).max() < 1e-9 and ttau[2, 0] == 0.0 and np.all(tR[1] == 0.0)
+        # a window outside the bundle is refused BEFORE anything is freed; the bundle stays usable
+        assert L.torj_bundle_set_window(bh, 2, 5, 100) != 0
+        _lib.check(L.torj_bundle_trace(bh, gpu_small.handle(ctx), None, 0.4, len(psi), dp(psi)))
+        _lib.check(L.torj_bundle_final_state(bh, dp(u), None, None, None))
+    finally:
+        L.torj_bundle_destroy(bh)
+    Rr, ph, ta = tj.cylindrical_state(np.array([[[3.0], [4.0], [1.0]]]), np.array([[np.exp(-2.0)]]))
+    assert Rr[0, 0] == 5.0 and abs(ta[0, 0] - 2.0) < 1e-15
+
+
+def test_left_grid_status_is_informational(gpu_small, oracle_small, gl24, launcher):
+    """Two 1.5 m segments: the ray crosses the plasma and the (R,Z) box within one segment and ends outside the grid, on the
+    splines' linear extrapolation, exactly as the reference would; status 3 flags it, results are still delivered."""
+    opt = tj.default_options(n_segments=2)
+    res = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 140e9, -1, 3.0, np.linspace(0, 1, 64),
+                          options=opt)
+    ro = oracle_small.make_ray(launcher["x0"], launcher["N0"], 140e9, -1, 3.0, np.linspace(0, 1, 64), gl24,
+                               opts=O.OracleOptions.default(n_segments=2))
+    assert list(res["status"]) == [3]                                      # TORJ_RAY_LEFT_GRID
+    assert res["n_points"][0] == len(ro["s"]) and abs(res["P_final"][0] - ro["P"][-1]) < 1e-10
+    assert res["counters"]["n_rays_ok"] == 1
+    s, u, P, prof, dep = tj.make_ray(gpu_small, launcher["x0"], launcher["N0"], 140e9, -1, 3.0, np.linspace(0, 1, 64), options=opt)
+    assert len(s) == len(ro["s"])                                          # informational: make_ray does not raise
+
+
+def test_quadrature_table_is_shared_per_device(gpu_small, launcher):
+    """abs_Al_init's table is one per device (the reference's module globals, src/constants.jl:7-8): a second context inherits
+    it, an identical re-init is free, and a different n takes effect for every context."""
+    L = tj.lib()
+    h = _lib.c_vp()
+    _lib.check(L.torj_ctx_create(0, None, C.byref(h)))
+    try:
+        one = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.5, PSI, ctx=h)   # inherited
+        ref = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.5, PSI)
+        assert one["P_final"][0] == ref["P_final"][0]
+        tj.abs_Al_init(12, h)
+        low = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.5, PSI)
+        assert low["P_final"][0] != ref["P_final"][0] and abs(low["P_final"][0] - ref["P_final"][0]) < 1e-3
+    finally:
+        tj.abs_Al_init(24)
+        L.torj_ctx_destroy(h)
+    again = tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.5, PSI)
+    assert again["P_final"][0] == ref["P_final"][0]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU front end: sharding modes, NCCL all-reduce on the device profiles / deterministic host sum
+# ------------------------------------------------------------------------------------------------------------------
+def test_multi_gpu_front_end_collective_and_sharding(gpu_small, launcher):
+    import torch
+    ndev = torch.cuda.device_count()
+    Ls = [dict(r=2.5, phi=0.0, z=0.4, steering_angle_pol=np.deg2rad(p), steering_angle_tor=t, spot_size=0.0174,
+               inverse_curvature_radius=1 / 3.99, f=95e9, mode=1) for p, t in ((30.0, 0.0), (20.0, 0.1), (38.0, -0.2), (26.0, 0.05), (33.0, 0.15))]
+    P, D, W, B = [], [], [], []
+    for b, q in enumerate(Ls):
+        p, d, w = tj.launch_peripheral_rays(np.array([2.5, 0.0, 0.4]), tj.pol_tor_angles_2_vector(q["steering_angle_pol"], q["steering_angle_tor"]),
+                                            0.0174, 1 / 3.99, 95e9, N_rings=3, min_azimuthal_points=5)
+        P.append(p); D.append(d); W.append(w / len(Ls)); B.append(np.full(len(w), b, dtype=np.int32))
+    pos, dirs, w, bid = np.concatenate(P), np.concatenate(D), np.concatenate(W), np.concatenate(B)
+    per = len(W[0])
+    psi = np.linspace(0, 1, 150)
+    one = tj.trace_bundle(gpu_small, pos, dirs, w, 95e9, 1, 0.6, psi, beam_id=bid, n_beams=len(Ls))
+    mg = tj.MultiGPU()
+    try:
+        assert mg.n_devices == ndev
+        mg.abs_Al_init(24)
+        for sharding, det in (("contiguous", False), ("block_cyclic", False), ("block_cyclic", True)):
+            mg.configure(sharding=sharding, block_rays=per, deterministic=det)
+            r = mg.trace_bundle(gpu_small, pos, dirs, w, 95e9, 1, 0.6, psi, beam_id=bid, n_beams=len(Ls))
+            assert mg.used_nccl == (ndev > 1 and not det), (sharding, det, ndev)
+            assert np.array_equal(r["n_points"], one["n_points"]) and np.array_equal(r["status"], one["status"])
+            assert np.abs(r["P_final"] - one["P_final"]).max() < 1e-11
+            assert np.abs(r["dP_dV"] - one["dP_dV"]).max() <= 1e-9 * np.abs(one["dP_dV"]).max()
+            assert np.abs(r["deposited_power"] - one["deposited_power"]).max() < 1e-11
+            assert r["counters"]["n_acc"] == one["counters"]["n_acc"]
+        with pytest.raises(tj.TorjError):
+            mg.configure(sharding="block_cyclic", block_rays=0)
+    finally:
+        mg.close()
+        tj.abs_Al_init(24)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# wider full-size parity
+# ------------------------------------------------------------------------------------------------------------------
+def test_config3_512_rays_against_oracle_and_scipy_deposition(gpu_full, oracle_full, gl24, launcher):
+    """512 rays spread evenly over the 65 543-ray bundle of configs[2], traced inside the full bundle: per-ray step counts and
+    final power against the oracle, the sub-bundle's profile against the oracle's faithful (spline-root) deposition, and — so
+    that this is not the kernel's deposition checked against its own restatement — one ray's profile recomputed by scipy's
+    FITPACK (splrep / sproot / splint = Dierckx) from the GPU's own trajectory samples, following src/plasma.jl:91-151."""
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=66, min_azimuthal_points=14)
+    n = len(w)
+    pick = np.linspace(0, n - 1, 512).astype(int)
+    res = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI)
+    ref = oracle_full.trace_bundle(pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, gl24, deposition="faithful",
+                                   also_streaming=True)
+    assert (ref["status"] == 0).all() and np.array_equal(res["n_points"][pick], ref["n_points"])
+    assert np.abs(res["P_final"][pick] - ref["P_final"]).max() < 1e-12
+    sub = tj.trace_bundle(gpu_full, pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, trajectories=(100, 1))
+    assert np.array_equal(sub["P_final"], res["P_final"][pick])        # a ray does not depend on its neighbours or its lane
+    assert abs(sub["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(sub["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL and l2rel(sub["dP_dV"], ref["dP_dV_streaming"]) < L2_LIKE
+    # independent deposition of ray 100 of the sub-bundle
+    m = int(sub["n_points"][100])
+    s, xyz, dPds = sub["traj_s"][0, :m], sub["traj_xyz"][0, :, :m], sub["traj_dP_ds"][0, :m]
+    psi_s = tj.evaluate_psi(gpu_full, xyz.T)
+    tck_p = interpolate.splrep(s, dPds, s=0, k=3)
+    shell = np.zeros(len(PSI))
+    for j in range(len(PSI) - 2, -1, -1):
+        r_lo = interpolate.sproot(interpolate.splrep(s, psi_s - PSI[j], s=0, k=3), mest=8)
+        r_hi = interpolate.sproot(interpolate.splrep(s, psi_s - PSI[j + 1], s=0, k=3), mest=8)
+        roots = np.sort(np.concatenate([r_lo, r_hi]))
+        if len(roots) < 2:
+            break
+        if len(roots) % 2:
+            roots = roots[:-1]
+        shell[j] = sum(abs(interpolate.splint(roots[k], roots[k + 1], tck_p)) for k in range(0, len(roots), 2))
+    dV = gpu_full.volume(PSI[1:]) - gpu_full.volume(PSI[:-1])
+    indep = np.concatenate([shell[:-1] / dV, [0.0]])
+    assert l2rel(sub["traj_dP_dV_ray"][0], indep) < L2_FAITHFUL
+    assert abs(float(np.sum(shell)) - sub["P_deposited_ray"][100]) < 1e-5
+
+
+def test_config4_full_sweep_rays_and_whole_beams(gpu_full, oracle_full, gl24):
+    """The full 1 049 600-ray sweep of configs[3] (32 x 32 launcher angles x 1 025 rays), one profile per beam, in one call:
+    256 rays spread over the whole sweep and 4 whole beams' profiles against the oracle."""
+    psi = np.linspace(0, 1, 200)
+    pols, tors = np.deg2rad(np.linspace(10.0, 40.0, 32)), np.deg2rad(np.linspace(-15.0, 15.0, 32))
+    Ls = [dict(r=2.5, phi=0.0, z=0.4, steering_angle_pol=p, steering_angle_tor=t, spot_size=0.0174,
+               inverse_curvature_radius=1 / 3.99, f=95e9, mode=1) for p in pols for t in tors]
+    dP, dep, W, Pf, res = tj.make_beams(gpu_full, Ls, 1.0, psi, N_rings=7, min_azimuthal_points=20)
+    n = len(res["status"])
+    assert n == 1049600 and dP.shape == (1024, 200)
+    ok = np.isin(res["status"], (0, 3))
+    assert ok.mean() > 0.9999
+    per = 1025
+
+    def rays_of(b):
+        N0 = tj.pol_tor_angles_2_vector(Ls[b]["steering_angle_pol"], Ls[b]["steering_angle_tor"])
+        return tj.launch_peripheral_rays(np.array([2.5, 0.0, 0.4]), N0, 0.0174, 1 / 3.99, 95e9, N_rings=7, min_azimuthal_points=20)
+
+    pick = np.linspace(0, n - 1, 256).astype(int)
+    P, D = [], []
+    for g in pick:
+        p, d, _ = rays_of(g // per)
+        P.append(p[g % per]); D.append(d[g % per])
+    ref = oracle_full.trace_bundle(np.array(P), np.array(D), np.ones(len(pick)), 95e9, 1, 1.0, psi, gl24, deposition="streaming")
+    good = ref["status"] == 0
+    assert np.array_equal(ok[pick], good)
+    assert np.array_equal(res["n_points"][pick][good], ref["n_points"][good])
+    assert np.abs(res["P_final"][pick][good] - ref["P_final"][good]).max() < 1e-11
+    for b in (0, 341, 682, 1023):
+        p, d, w = rays_of(b)
+        rb = oracle_full.trace_bundle(p, d, w, 95e9, 1, 1.0, psi, gl24, deposition="faithful", also_streaming=True)
+        if (rb["status"] != 0).any():
+            continue
+        assert abs(dep[b] - rb["deposited_power"]) <= FRAC_TOL * max(rb["deposited_power"], 1e-3)
+        if rb["deposited_power"] > 1e-6:
+            assert l2rel(dP[b], rb["dP_dV"]) < L2_FAITHFUL and l2rel(dP[b], rb["dP_dV_streaming"]) < L2_LIKE
