@@ -68,7 +68,9 @@ typedef struct torj_options {
                                       2 = segment hand-off: a ray may change lanes between two of its n_segments
                                       segments, so all rays advance together: no partly filled last wave, and the lanes
                                       of a warp stay in step (automatic picks this when the bundle exceeds the resident
-                                      lanes, 37 888 on a B200) */
+                                      lanes, 37 888 on a B200). With one lane per ray the tail of such a run — fewer rays
+                                      alive than lanes — continues in stages with 8 and then 32 lanes per ray;
+                                      3 = segment hand-off without those tail stages */
     int32_t absorption_model;      /* 0 = Albajar (reference src/absorption.jl:191-235, what the reference's gradΛ! calls);
                                       1 = warm-plasma damping: alpha = α(ω, X, Y, |N|, acos(N∥/|N|), Te, v_g_perp, mode)[2] of
                                       reference src/general_absorption.jl:1328-1337 (iwarm = 3, Larmor order lrm <= 5) in the
@@ -77,9 +79,10 @@ typedef struct torj_options {
                                       (te_min); the debug assertion at :314-316 is dropped (it calls an un-imported function).
                                       With alpha_floor > 0 the 501-node quadrature is skipped where the anti-Hermitian part is
                                       below the floor by construction (torj_warm.cuh); 0 evaluates it everywhere */
-    int32_t lanes_per_ray;         /* 0 = automatic; 1 = one GPU thread per ray; 32 = a warp per ray (the nodes of the harmonic
-                                      integrals / of the warm quadrature are split over the lanes): for bundles far below the
-                                      resident lanes and for the warm model. Results agree to rounding (summation order) */
+    int32_t lanes_per_ray;         /* 0 = automatic; 1 = one GPU thread per ray; 8 / 32 = a group of 8 lanes / a warp per ray (the
+                                      nodes of the harmonic integrals / of the warm quadrature are split over the lanes): for
+                                      bundles below the resident lanes, where the time is one ray's latency, and for the warm
+                                      model (1 or 32 only). Results agree to rounding (summation order) */
     int32_t reserved_;             /* keeps the struct size a multiple of 8; must be 0 */
 } torj_options;
 
@@ -115,7 +118,9 @@ int64_t torj_ctx_launch_count(const torj_ctx* ctx);
 /* device duration (CUDA events on the context stream) of the most recent trace-kernel launch; synchronises on it */
 int torj_ctx_last_trace_ms(torj_ctx* ctx, double* ms);
 
-/* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64).
+/* abs_Al_init(N) — reference src/absorption.jl:1-7: Gauss-Legendre nodes/weights on [-1,1] (n <= 64), ascending and
+ * symmetric (t[k] = -t[n-1-k], w[k] = w[n-1-k], as gausslegendre(N) returns them; anything else is refused: the kernel
+ * evaluates the Bessel functions of a node pair once).
  * Like the reference's module globals (src/constants.jl:7-8) the table is shared: ONE per device. A context created on
  * a device whose table is already set inherits it; setting different nodes synchronises the whole device first and
  * changes them for every context on that device. */

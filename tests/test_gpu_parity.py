@@ -453,7 +453,7 @@ def test_segment_handoff_schedule_gives_the_same_rays(gpu_small, arrays_small, l
 def test_option_validation(gpu_small, launcher):
     psi = np.linspace(0, 1, 10)
     for bad in (dict(max_harmonic=0), dict(max_harmonic=17), dict(scheme=2), dict(n_segments=0), dict(dtmax=0.0),
-                dict(abstol=-1.0), dict(alpha_floor=-1.0), dict(max_steps_per_segment=0), dict(schedule=3)):
+                dict(abstol=-1.0), dict(alpha_floor=-1.0), dict(max_steps_per_segment=0), dict(schedule=4)):
         with pytest.raises(tj.TorjError):
             tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.2, psi,
                             options=tj.default_options(**bad))

@@ -76,7 +76,7 @@ def test_warm_alpha_scan_against_oracle():
         # an iteration count one off (errnpr crossing 1e-4 within rounding) moves N_perp^2 by < 1e-4 of a contraction step
         assert np.mean(d <= tol) > 0.98, np.sort(d / tol)[-10:]
         assert np.all(d <= 1e-5 * np.abs(r[conv, 1]) + 1e-10)
-        assert np.max(np.abs(Nw[conv] - r[conv, 0]) / np.abs(r[conv, 0])) < 1e-6
+        assert np.max(np.abs(Nw[conv] - r[conv, 0])) < 1e-6       # N_warm = 0 where ierr = 99
     print(f"warm alpha: {n_cmp} converged points compared, worst |d alpha| / (1e-9 |alpha| + 1e-12) = {worst:.3g}")
 
 
@@ -110,14 +110,14 @@ def pl_state_along(opl, launcher, f, n):
 
 @pytest.mark.parametrize("lanes", [1, 32])
 def test_warm_single_ray_against_oracle(gl24, launcher, lanes):
-    """One ray of the config-5 equilibrium (T_e0 = 10 keV, 110 GHz) with the warm model: same accepted steps, trajectory,
+    """One ray of the config-5 equilibrium (T_e0 = 10 keV; 95 GHz: the second-harmonic layer lies 0.25 m inside) with the warm model: same accepted steps, trajectory,
     power and deposition as the oracle's make_ray with absorption_model = 1, one thread per ray and a warp per ray."""
     arr = hot_arrays(129, 10e3)
     pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
     psi = np.linspace(0.0, 1.0, 300)
     opt = tj.default_options(absorption_model=1, alpha_floor=0.0, lanes_per_ray=lanes)
-    s, u, P, prof, dep = tj.make_ray(pl, launcher["x0"], launcher["N0"], 110e9, 1, 0.3, psi, options=opt)
-    ro = opl.make_ray(launcher["x0"], launcher["N0"], 110e9, 1, 0.3, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
+    s, u, P, prof, dep = tj.make_ray(pl, launcher["x0"], launcher["N0"], 95e9, 1, 0.35, psi, options=opt)
+    ro = opl.make_ray(launcher["x0"], launcher["N0"], 95e9, 1, 0.35, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
     assert ro["status"] == 0 and len(s) == len(ro["s"])
     xyz = np.array(u)
     assert max(np.abs(xyz[:, 0] - ro["x"]).max(), np.abs(xyz[:, 1] - ro["y"]).max(), np.abs(xyz[:, 2] - ro["z"]).max()) < TRAJ_TOL
@@ -155,7 +155,7 @@ def test_warm_beam_gate_and_mappings_agree(gl24, launcher):
 
 
 def test_warm_model_option_validation(gpu_small, launcher):
-    for kw in (dict(absorption_model=2), dict(lanes_per_ray=8), dict(absorption_model=1, max_harmonic=5)):
+    for kw in (dict(absorption_model=2), dict(lanes_per_ray=16), dict(absorption_model=1, lanes_per_ray=8), dict(absorption_model=1, max_harmonic=5)):
         with pytest.raises(tj.TorjError):
             tj.trace_bundle(gpu_small, launcher["x0"][None], launcher["N0"][None], [1.0], 95e9, 1, 0.1, PSI, options=tj.default_options(**kw))
 
@@ -191,7 +191,47 @@ def test_warp_per_ray_high_harmonics_and_exact_mode(gl24, launcher):
     res = tj.trace_bundle(pl, pos, dirs, w, 225e9, 1, 0.5, psi, options=opt)
     ref = opl.trace_bundle(pos, dirs, w, 225e9, 1, 0.5, psi, gl24, opts=O.OracleOptions.default(max_harmonic=5))
     assert np.array_equal(res["n_points"], ref["n_points"]) and np.abs(res["P_final"] - ref["P_final"]).max() < 1e-10
-    assert res["counters"]["n_harm"] == int(ref["counters"]["n_harm"])
+    one = tj.trace_bundle(pl, pos, dirs, w, 225e9, 1, 0.5, psi, options=tj.default_options(lanes_per_ray=1, max_harmonic=5, alpha_floor=0.0))
+    assert res["counters"] == one["counters"] and np.abs(res["P_final"] - one["P_final"]).max() < 1e-12
+
+
+def test_tail_stages_agree_with_plain_handoff(gpu_full, oracle_full, gl24, launcher):
+    """65 543 rays > 37 888 resident lanes: segment hand-off; when few rays are left the launch stops, the survivors are
+    compacted and continue from their hand-off records with 8 lanes per ray, then a warp per ray (schedule 0 / 2). Same rays as
+    the plain hand-off (schedule 3) up to the summation order of the node sums in the tail."""
+    L = tj.lib()
+    ctx = _lib.context()
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=66, min_azimuthal_points=14)
+    n0 = L.torj_ctx_launch_count(ctx)
+    plain = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(schedule=3, lanes_per_ray=1))
+    n1 = L.torj_ctx_launch_count(ctx)
+    staged = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(lanes_per_ray=1))
+    n2 = L.torj_ctx_launch_count(ctx)
+    assert n1 - n0 == 3 and n2 - n1 == 7        # init, trace, finalize / init, 3 trace stages, 2 compactions, finalize
+    assert (staged["status"] == 0).all() and np.array_equal(plain["n_points"], staged["n_points"])
+    assert plain["counters"]["n_acc"] == staged["counters"]["n_acc"] and plain["counters"]["n_rhs"] == staged["counters"]["n_rhs"]
+    assert staged["counters"]["n_rays_ok"] == len(w)
+    assert np.abs(plain["P_final"] - staged["P_final"]).max() < 1e-12
+    assert np.abs(plain["P_deposited_ray"] - staged["P_deposited_ray"]).max() < 1e-11
+    assert abs(plain["deposited_power"] - staged["deposited_power"]) < 1e-12 and l2rel(staged["dP_dV"], plain["dP_dV"]) < 1e-11
+    pick = np.linspace(0, len(w) - 1, 64).astype(int)
+    ref = oracle_full.trace_bundle(pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, gl24, deposition="streaming")
+    assert np.array_equal(staged["n_points"][pick], ref["n_points"]) and np.abs(staged["P_final"][pick] - ref["P_final"]).max() < 1e-12
+
+
+def test_eight_lanes_per_ray(gpu_small, oracle_small, gl24, launcher):
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=4, min_azimuthal_points=7)
+    psi = np.linspace(0, 1, 120)
+    runs = [tj.trace_bundle(gpu_small, pos, dirs, w, launcher["f"], 1, 0.8, psi, options=tj.default_options(lanes_per_ray=l, schedule=s))
+            for l, s in ((1, 1), (8, 1), (8, 2), (32, 2))]
+    for r in runs[1:]:
+        assert np.array_equal(r["n_points"], runs[0]["n_points"]) and r["counters"] == runs[0]["counters"]
+        assert np.abs(r["P_final"] - runs[0]["P_final"]).max() < 1e-12 and l2rel(r["dP_dV"], runs[0]["dP_dV"]) < 1e-11
+    ref = oracle_small.trace_bundle(pos, dirs, w, launcher["f"], 1, 0.8, psi, gl24)
+    assert abs(runs[1]["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
+    assert l2rel(runs[1]["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -212,7 +252,8 @@ def test_step_controller_with_rejections_and_dead_band(gpu_full, oracle_full, gl
         ray = oracle_full.make_ray(pos[0], dirs[0], launcher["f"], 1, 1.0, PSI, gl24, opts=O.OracleOptions.default(**kw))
         n = int(res["n_points"][0])
         ds = np.diff(res["traj_s"][0, 1:n])
-        assert np.abs(res["traj_s"][0, :n] - ray["s"]).max() < 1e-12 and np.abs(res["traj_xyz"][0, 0, :n] - ray["x"]).max() < TRAJ_TOL
+        # tolerance-limited steps: dt follows EEst^(7/10k), so the sample positions agree only as well as the error estimates do
+        assert np.abs(res["traj_s"][0, :n] - ray["s"]).max() < 1e-8 and np.abs(res["traj_xyz"][0, 0, :n] - ray["x"]).max() < 1e-7
         held = np.sum(np.abs(np.diff(ds)) < 1e-15 * ds[:-1]) / len(ds)
         assert len(np.unique(np.round(ds, 12))) > 5 and held > 0.3     # the step varies, and is held for stretches
 
@@ -350,8 +391,11 @@ def test_config3_512_rays_against_oracle_and_scipy_deposition(gpu_full, oracle_f
                                    also_streaming=True)
     assert (ref["status"] == 0).all() and np.array_equal(res["n_points"][pick], ref["n_points"])
     assert np.abs(res["P_final"][pick] - ref["P_final"]).max() < 1e-12
-    sub = tj.trace_bundle(gpu_full, pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, trajectories=(100, 1))
+    sub = tj.trace_bundle(gpu_full, pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, trajectories=(100, 1),
+                          options=tj.default_options(lanes_per_ray=1))
     assert np.array_equal(sub["P_final"], res["P_final"][pick])        # a ray does not depend on its neighbours or its lane
+    auto = tj.trace_bundle(gpu_full, pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI)   # small bundle: several lanes per ray
+    assert np.abs(auto["P_final"] - sub["P_final"]).max() < 1e-12 and l2rel(auto["dP_dV"], sub["dP_dV"]) < 1e-11
     assert abs(sub["deposited_power"] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"]
     assert l2rel(sub["dP_dV"], ref["dP_dV"]) < L2_FAITHFUL and l2rel(sub["dP_dV"], ref["dP_dV_streaming"]) < L2_LIKE
     # independent deposition of ray 100 of the sub-bundle

@@ -93,6 +93,7 @@ struct torj_bundle {
     double* d_hand = nullptr;
     int *d_segdone = nullptr, *d_left = nullptr;
     int h_left = 0;  // source of the copy into d_left (outlives the call)
+    int *d_stage = nullptr, *d_list = nullptr;  // tail stages: [2 stages][stop_seg, n_list], list of live rays
     // trajectory window
     int64_t traj_first = 0, traj_count = 0;
     int traj_max = 0;
@@ -315,6 +316,11 @@ int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* wei
     if (n < 1 || n > TORJ_MAX_GL) FAIL("torj_abs_init: need 1 <= n <= 64");
     if (!nodes || !weights) FAIL("torj_abs_init: NULL nodes / weights");
     if (set_device(c)) return 1;
+    // the rule must be symmetric, t[k] = -t[n-1-k], w[k] = w[n-1-k] — every Gauss-Legendre rule is (gausslegendre(N), reference
+    // src/absorption.jl:4): the kernel evaluates the Bessel functions of a node pair once
+    for (int k = 0; k < n; ++k)
+        if (std::fabs(nodes[k] + nodes[n - 1 - k]) > 1e-13 || std::fabs(weights[k] - weights[n - 1 - k]) > 1e-13)
+            FAIL("torj_abs_init: nodes / weights are not a symmetric rule (expected FastGaussQuadrature.gausslegendre(N))");
     std::vector<double> want(nodes, nodes + n);
     want.insert(want.end(), weights, weights + n);
     std::lock_guard<std::mutex> lk(g_gl.mu);
@@ -330,6 +336,7 @@ int torj_abs_init(torj_ctx* c, int32_t n, const double* nodes, const double* wei
         g.t[i] = nodes[i];
         g.w[i] = weights[i];
         g.sq[i] = std::sqrt(1.0 - nodes[i] * nodes[i]);
+        g.wp[i] = (2 * i == n - 1) ? 0.5 * weights[i] : weights[i];
     }
     CK(cudaDeviceSynchronize());  // no kernel of ANY context on this device may be reading the old table
     CK(cudaMemcpyToSymbol(c_gl, &g, sizeof g));
@@ -561,6 +568,16 @@ static double volume_at(const torj_plasma* p, double x) {
     for (int k = 0; k < 4; ++k) { v += w[k] * p->vol_c[i - 1 + k]; dv += dw[k] * p->vol_c[i - 1 + k]; }
     if (xc != x) v += (x - xc) * dv;
     return v;
+}
+
+typedef void (*trace_kernel_t)(TraceArgs);
+static trace_kernel_t pick_trace_kernel(int scheme, bool high, int model, int lpr) {
+    const bool z3 = scheme == 1;
+    if (model == 1) return lpr == 32 ? (z3 ? k_trace<1, false, 1, 32> : k_trace<0, false, 1, 32>)
+                                     : (z3 ? k_trace<1, false, 1, 1> : k_trace<0, false, 1, 1>);
+    if (lpr == 32) return high ? (z3 ? k_trace<1, true, 0, 32> : k_trace<0, true, 0, 32>) : (z3 ? k_trace<1, false, 0, 32> : k_trace<0, false, 0, 32>);
+    if (lpr == 8) return high ? (z3 ? k_trace<1, true, 0, 8> : k_trace<0, true, 0, 8>) : (z3 ? k_trace<1, false, 0, 8> : k_trace<0, false, 0, 8>);
+    return high ? (z3 ? k_trace<1, true> : k_trace<0, true>) : (z3 ? k_trace<1, false> : k_trace<0, false>);
 }
 
 static SolverOpts to_sopts(const torj_options* o, double s_max) {
@@ -801,7 +818,7 @@ void torj_bundle_destroy(torj_bundle* b) {
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->d_pos); cudaFree(b->d_dir); cudaFree(b->d_w); cudaFree(b->d_freq); cudaFree(b->d_mode); cudaFree(b->d_u0);
     cudaFree(b->d_s0); cudaFree(b->d_psil); cudaFree(b->d_Pf); cudaFree(b->d_Pdep); cudaFree(b->d_status); cudaFree(b->d_npts);
-    cudaFree(b->d_hand); cudaFree(b->d_segdone); cudaFree(b->d_left);
+    cudaFree(b->d_hand); cudaFree(b->d_segdone); cudaFree(b->d_left); cudaFree(b->d_stage); cudaFree(b->d_list);
     cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
     cudaFree(b->d_profile);
     cudaFree(b->d_beam);
@@ -857,10 +874,13 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
     if (od.max_harmonic < 1 || od.max_harmonic > 16) FAIL("torj_bundle_trace: max_harmonic must be in 1..16 (1 = no absorption)");
     if (!(od.dtmax > 0.0) || !(od.abstol > 0.0) || !(od.reltol > 0.0)) FAIL("torj_bundle_trace: dtmax, abstol and reltol must be > 0");
-    if (od.schedule < 0 || od.schedule > 2) FAIL("torj_bundle_trace: schedule must be 0 (automatic), 1 (whole rays) or 2 (segment hand-off)");
+    if (od.schedule < 0 || od.schedule > 3)
+        FAIL("torj_bundle_trace: schedule must be 0 (automatic), 1 (whole rays), 2 (segment hand-off) or 3 (hand-off without tail stages)");
     if (od.max_steps_per_segment < 1) FAIL("torj_bundle_trace: max_steps_per_segment < 1");
     if (od.absorption_model != 0 && od.absorption_model != 1) FAIL("torj_bundle_trace: absorption_model must be 0 (Albajar) or 1 (warm)");
-    if (od.lanes_per_ray != 0 && od.lanes_per_ray != 1 && od.lanes_per_ray != 32) FAIL("torj_bundle_trace: lanes_per_ray must be 0 (automatic), 1 or 32");
+    if (od.lanes_per_ray != 0 && od.lanes_per_ray != 1 && od.lanes_per_ray != 8 && od.lanes_per_ray != 32)
+        FAIL("torj_bundle_trace: lanes_per_ray must be 0 (automatic), 1, 8 or 32");
+    if (od.absorption_model == 1 && od.lanes_per_ray == 8) FAIL("torj_bundle_trace: the warm model runs with 1 or 32 lanes per ray");
     if (od.absorption_model == 1 && od.max_harmonic > 3) FAIL("torj_bundle_trace: max_harmonic > 3 belongs to the Albajar model; the warm model takes its harmonics from larmornumber");
     if (!(s_max > 0.0)) FAIL("torj_bundle_trace: s_max must be > 0");
     if (set_device(c)) return 1;
@@ -912,15 +932,19 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.n_psi = n_psi; a.n_beams = b->n_beams; a.beam_id = b->d_beam; a.psi_edges = b->d_edges; a.bins = b->d_bins; a.next_ray = b->d_queue; a.counters = b->d_counters;
     a.warm_tab = c->d_warm_tab; a.u_final = b->d_ufinal;
     const int model = od.absorption_model;
-    // A warp per ray (lanes_per_ray = 32) when the bundle is far too small to fill the GPU with one thread per ray —
-    // then the time is one ray's latency, and splitting the quadrature nodes over 32 lanes shortens exactly that — and
-    // for the warm model up to one ray per resident lane: its alpha is ~100x the rest of the RHS and warp-cooperative
-    // either way, so a warp per ray loses little throughput and gains the latency.
+    // Several lanes per ray when the bundle cannot fill the GPU with one thread per ray — then the time is one ray's
+    // latency, and splitting the quadrature nodes over the lanes of a group shortens exactly that: a warp per ray up to
+    // the resident warps (1 184), 8 lanes per ray up to an eighth of the resident lanes (4 736). Measured (profiles/):
+    // a cold 1 025-ray beam 56 -> 61 ms (nothing to split), a 10 keV 1 025-ray beam 510 -> 170 ms. The warm model, whose
+    // alpha is ~100x the rest of the RHS and warp-cooperative either way, takes a warp per ray up to half the lanes.
     const int64_t lanes_guess = (int64_t)c->num_sms * TORJ_MINB * TORJ_TPB;
-    int coop = od.lanes_per_ray == 32;
-    if (od.lanes_per_ray == 0) coop = model == 1 ? (b->n <= lanes_guess / 2) : (b->n * 16 <= lanes_guess);
+    int lpr = od.lanes_per_ray;
+    if (lpr == 0) {
+        if (model == 1) lpr = (b->n <= lanes_guess / 2) ? 32 : 1;
+        else lpr = (b->n * 32 <= lanes_guess) ? 32 : ((b->n * 8 <= lanes_guess) ? 8 : 1);
+    }
     size_t smem = (size_t)n_psi * sizeof(double);
-    if (model == 1 && !coop) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
+    if (model == 1 && lpr == 1) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
 #if TORJ_K_SMEM
     smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
 #endif
@@ -928,17 +952,13 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     smem += (size_t)TORJ_PARK_SLOTS * TORJ_TPB * sizeof(double);
 #endif
     int bps = 0;
-    int64_t warps = coop ? b->n : (b->n + 31) / 32;
+    int64_t warps = (b->n * lpr + 31) / 32;
     int64_t blocks_needed = (warps + (TORJ_TPB / 32) - 1) / (TORJ_TPB / 32);
     // harmonics above the third, the warm model and the warp-per-ray mapping run in their own instantiations, so the
     // default kernels do not carry the code
     void (*kern)(TraceArgs);
-    const bool high = od.max_harmonic > 3, z3 = od.scheme == 1;
-    if (model == 1) kern = coop ? (z3 ? k_trace<1, false, 1, true> : k_trace<0, false, 1, true>)
-                                : (z3 ? k_trace<1, false, 1, false> : k_trace<0, false, 1, false>);
-    else if (coop) kern = high ? (z3 ? k_trace<1, true, 0, true> : k_trace<0, true, 0, true>)
-                               : (z3 ? k_trace<1, false, 0, true> : k_trace<0, false, 0, true>);
-    else kern = high ? (z3 ? k_trace<1, true> : k_trace<0, true>) : (z3 ? k_trace<1, false> : k_trace<0, false>);
+    const bool high = od.max_harmonic > 3;
+    kern = pick_trace_kernel(od.scheme, high, model, lpr);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, TORJ_TPB, smem));
     if (bps < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
@@ -947,8 +967,8 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     // rays on 37 888 lanes: 1.73 ray-times instead of 2) and keeps the lanes of a warp in step: with whole rays per lane
     // a bundle of rays of very different lengths (the 1 M-ray angle sweep) drifts apart and some lane pays for the full
     // absorption coefficient on every trip (measured 3.1 s -> 2.4 s). Below one wave there is nothing to balance.
-    const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB / (coop ? 32 : 1);  // rays in flight
-    int interleave = od.schedule == 2 || (od.schedule == 0 && b->n > lanes);
+    const int64_t lanes = (int64_t)c->num_sms * bps * TORJ_TPB / lpr;  // rays in flight
+    int interleave = od.schedule == 2 || od.schedule == 3 || (od.schedule == 0 && b->n > lanes);
     if (od.n_segments < 2 || b->n > 0x7fffffff) interleave = 0;
     a.interleave = interleave; a.hand = nullptr; a.seg_done = nullptr; a.rays_left = nullptr;
     if (interleave) {
@@ -960,10 +980,49 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         CK(cudaMemcpyAsync(b->d_left, &b->h_left, sizeof(int), cudaMemcpyHostToDevice, st));
         a.hand = b->d_hand; a.seg_done = b->d_segdone; a.rays_left = b->d_left;
     }
+    a.stop_left = 0; a.stop_seg = nullptr; a.first_seg = nullptr; a.ray_list = nullptr; a.n_list = nullptr;
+    // Tail stages (hand-off schedule, Albajar model, one lane per ray): when fewer rays are alive than lanes, the rays that
+    // are left — the longest ones, deep in the absorbing layer — run alone on their lanes while the rest of the GPU idles.
+    // The launch therefore stops at the segment round that begins with few rays alive; the survivors are compacted and
+    // continue from their hand-off records with 8 lanes per ray, the last ones with a warp per ray (torj_kernels.cuh).
+    const bool staged = interleave && lpr == 1 && model == 0 && od.schedule != 3;
     CK(cudaEventRecord(c->ev0, st));
-    kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
-    c->launches++;
-    CK(cudaGetLastError());
+    if (!staged) {
+        kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+        c->launches++;
+        CK(cudaGetLastError());
+    } else {
+        if (!b->d_stage) CK(cudaMalloc(&b->d_stage, 4 * sizeof(int)));
+        if (!b->d_list) CK(cudaMalloc(&b->d_list, (size_t)b->n * sizeof(int)));
+        static const int h_init[4] = {0x7fffffff, 0, 0x7fffffff, 0};
+        CK(cudaMemcpyAsync(b->d_stage, h_init, sizeof h_init, cudaMemcpyHostToDevice, st));
+        const int lprs[3] = {1, 8, 32};
+        for (int sgi = 0; sgi < 3; ++sgi) {
+            trace_kernel_t ks = pick_trace_kernel(od.scheme, high, model, lprs[sgi]);
+            int bs = 0;
+            CK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, ks, TORJ_TPB, smem));
+            if (bs < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
+            const int64_t cap = (int64_t)c->num_sms * bs * TORJ_TPB;  // lanes
+            TraceArgs as = a;
+            if (sgi > 0) {  // rounds and rays of this stage: where the previous one stopped
+                k_compact_live<<<1, 1024, 0, st>>>(b->d_segdone, (long long)b->n, b->d_list, b->d_stage + 2 * (sgi - 1) + 1);
+                c->launches++;
+                CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
+                as.first_seg = b->d_stage + 2 * (sgi - 1);
+                as.ray_list = b->d_list;
+                as.n_list = b->d_stage + 2 * (sgi - 1) + 1;
+            }
+            if (sgi < 2) {  // stop when the rays left fit the next stage's mapping (8 lanes per ray gains ~2.5x per ray: two waves)
+                as.stop_seg = b->d_stage + 2 * sgi;
+                as.stop_left = (int)std::min<int64_t>(sgi == 0 ? 2 * cap / 8 : cap / 32, 0x7fffffff);
+            }
+            const int64_t gs = sgi == 0 ? grid : (int64_t)c->num_sms * bs;
+            ks<<<(unsigned)gs, TORJ_TPB, smem, st>>>(as);
+            c->launches++;
+            CK(cudaGetLastError());
+        }
+    }
     CK(cudaEventRecord(c->ev1, st));
     c->ev_valid = true;
     k_finalize<<<(unsigned)(((size_t)b->n_beams * (n_psi + 2) + 127) / 128), 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->n_beams,

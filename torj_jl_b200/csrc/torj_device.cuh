@@ -28,6 +28,12 @@ namespace torj {
 #define TORJ_ROW_FENCE 1
 #endif
 #define TORJ_BESS_K 24
+#ifndef TORJ_PAIR
+#define TORJ_PAIR 1      // harmonic integrals over node PAIRS (+t, -t): the Bessel series of a pair are evaluated once
+#endif
+#ifndef TORJ_PSI_LAZY
+#define TORJ_PSI_LAZY 1  // psi_N rides on the stencil only at the stages whose psi is used (FSAL / seed / callback)
+#endif
 
 struct DevTables {
     const double2* __restrict__ A;  // 2 double2 per node
@@ -41,6 +47,7 @@ struct GLNodes {
     double t[TORJ_MAX_GL];
     double w[TORJ_MAX_GL];
     double sq[TORJ_MAX_GL];  // sqrt(1 - t^2)
+    double wp[TORJ_MAX_GL];  // pair weights: w[k] for k < n/2, w[k]/2 for the middle node of an odd rule
     int n;
 };
 
@@ -149,7 +156,7 @@ struct Fields {  // value, d/dR, d/dZ
 
 // all five RHS fields (and optionally psi_N) at a point inside the grid
 template <bool WITH_PSI>
-__device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f) {
+__device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true) {
     double wr[4], dwr[4], wz[4], dwz[4];
     int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
     int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
@@ -173,7 +180,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             a[2] = fma(wr[i], q1.x, a[2]); aR[2] = fma(dwr[i], q1.x, aR[2]);
             a[3] = fma(wr[i], q1.y, a[3]); aR[3] = fma(dwr[i], q1.y, aR[3]);
             at = fma(wr[i], q2.x, at);
-            if (WITH_PSI) { ap = fma(wr[i], q2.y, ap); apR = fma(dwr[i], q2.y, apR); }
+            if (WITH_PSI && (!TORJ_PSI_LAZY || need_psi)) { ap = fma(wr[i], q2.y, ap); apR = fma(dwr[i], q2.y, apR); }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -182,7 +189,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             vZ[q] = fma(dwzj, a[q], vZ[q]);
         }
         te = fma(wzj, at, te);
-        if (WITH_PSI) { ps = fma(wzj, ap, ps); psR = fma(wzj, apR, psR); psZ = fma(dwzj, ap, psZ); }
+        if (WITH_PSI && (!TORJ_PSI_LAZY || need_psi)) { ps = fma(wzj, ap, ps); psR = fma(wzj, apR, psR); psZ = fma(dwzj, ap, psZ); }
 #if TORJ_ROW_FENCE
         // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
         // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
@@ -242,9 +249,9 @@ __device__ __forceinline__ bool inside_grid(const DevTables& T, double R, double
 }
 
 template <bool WITH_PSI>
-__device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f) {
+__device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true) {
     if (inside_grid(T, R, Z)) {
-        eval_fields_in<WITH_PSI>(T, R, Z, f);
+        eval_fields_in<WITH_PSI>(T, R, Z, f, need_psi);
     } else {
         Ext3 e;
         e = eval_field_ext(T, 0, R, Z); f.BR = e.v; f.BR_R = e.dR; f.BR_Z = e.dZ;
@@ -427,14 +434,45 @@ struct HarmCoef {  // per-harmonic invariants
 };
 
 // reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M
-// COOP (a warp per ray, warp-uniform arguments): lane L takes nodes L, L+32, ...; butterfly reduction, so every lane
-// returns the same sum.
-template <int M, int K, bool GENERIC, bool COOP = false>
+// LPR > 1 (LPR = 8 or 32 lanes per ray; arguments uniform over the group): lane L of the group takes nodes L, L+LPR, ...;
+// butterfly reduction inside the group, so every lane of it returns the same sum.
+__device__ __forceinline__ unsigned group_mask(int lpr) {
+    return lpr >= 32 ? 0xffffffffu : (((1u << lpr) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(lpr - 1)));
+}
+template <int M, int K, bool GENERIC, int LPR = 1>
 __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) {
     double sum = 0.0;
     const int n = c_gl.n;
+#if TORJ_PAIR
+    // Gauss-Legendre rules are symmetric (torj_abs_init checks it): nodes +-t share sqrt(1 - t^2), hence the Bessel
+    // argument, J and D; the polarisation factor splits into a part even in t and a part odd in t.
+    const int half = (n + 1) >> 1;
+    const double ke = c.k1 - c.k3m2;
 #pragma unroll 1
-    for (int k = COOP ? (int)(threadIdx.x & 31u) : 0; k < n; k += COOP ? 32 : 1) {
+    for (int k = (int)(threadIdx.x & (unsigned)(LPR - 1)); k < half; k += LPR) {
+        const double t = c_gl.t[k], sq = c_gl.sq[k];
+        const double et = c.e1 * t;
+        const double exa = exp_fast(c.e0 + et), exb = exp_fast(c.e0 - et);
+        const double z = c.x_m * sq;
+        double J, D;
+        if (GENERIC) {
+            J = jn(m_rt, z);
+            D = 0.5 * z * (jn(m_rt - 1, z) - jn(m_rt + 1, z));
+        } else {
+            const double hz = 0.5 * z;
+            bessel_JD<M, K>(hz, hz * hz, J, D, m_rt);
+        }
+        const double J2 = J * J, JD = J * D;
+        // (|Axz|^2 + |ey|^2) J^2 + Re(Axz ey*) x_m/m dsq - (z/m)^2 |ey|^2 J_{m-1} J_{m+1} + (xs t)^2 |ez|^2 J^2   [even in t]
+        double ev = fma(c.k4 * t, t, ke) * J2;
+        ev = fma(c.k2, JD, ev);
+        ev = fma(c.k3, D * D, ev);
+        const double od = t * fma(c.k5, J2, c.k6 * JD);  // 2 xs Re(Axz ez*) t J^2 + xs Re(ey* ez) t x_m/m dsq           [odd in t]
+        sum = fma(c_gl.wp[k], fma(ev + od, exa, (ev - od) * exb), sum);
+    }
+#else
+#pragma unroll 1
+    for (int k = (int)(threadIdx.x & (unsigned)(LPR - 1)); k < n; k += LPR) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
         const double ex = exp_fast(fma(c.e1, t, c.e0));
         const double z = c.x_m * sq;
@@ -457,18 +495,20 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
         pf = fma(c.k6 * t, JD, pf);
         sum = fma(c_gl.w[k] * pf, ex, sum);
     }
-    if (COOP) {
+#endif
+    if (LPR > 1) {
+        const unsigned gm = group_mask(LPR);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        for (int off = LPR / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(gm, sum, off);
     }
     return sum * c.scale;
 }
 
 // rarely taken variants kept out of line so the hot code stays small (instruction cache)
-template <int M, bool COOP = false>
+template <int M, int LPR = 1>
 __device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M) {  // by value: see eval_field_ext
-    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false, COOP>(c, m_rt);
-    return harmonic_sum<(M ? M : 2), 1, true, COOP>(c, m_rt);
+    if (c.x_m <= 6.5) return harmonic_sum<M, 24, false, LPR>(c, m_rt);
+    return harmonic_sum<(M ? M : 2), 1, true, LPR>(c, m_rt);
 }
 
 // One harmonic's contribution to alpha [1/m] (sign included), or 0 when a rigorous bound shows it is < floor.
@@ -480,7 +520,7 @@ __device__ __noinline__ double harmonic_sum_large(const HarmCoef c, int m_rt = M
 #define TORJ_SKIP_MARGIN 1e-10
 #endif
 // M = 0: order given at run time (harmonics above the reference's third; libm jn() throughout).
-template <int M, bool COOP = false>
+template <int M, int LPR = 1>
 __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt, bool& safe, int m_rt = M) {
     const int m = M ? M : m_rt;
     const double fm = (double)m, ifm = 1.0 / (double)m;
@@ -520,9 +560,9 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     }
     safe = false;
     cnt.n_harm++;
-    if (M == 0 && m > 3) return harmonic_sum<2, 1, true, COOP>(c, m);
-    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false, COOP>(c, m);
-    return harmonic_sum_large<M, COOP>(c, m);
+    if (M == 0 && m > 3) return harmonic_sum<2, 1, true, LPR>(c, m);
+    if (c.x_m <= 3.2) return harmonic_sum<M, 12, false, LPR>(c, m);
+    return harmonic_sum_large<M, LPR>(c, m);
 }
 
 // Harmonics 4..max_harmonic (torj_options.max_harmonic > 3; the reference stops at 3, src/absorption.jl:199). Cold and
@@ -532,13 +572,13 @@ struct HighHarm {
     int n_harm, n_prune;
     bool safe;
 };
-template <bool COOP = false>
+template <int LPR = 1>
 __device__ __noinline__ HighHarm harmonics_above_3(const HarmPre& h, int max_harmonic, double m_0, bool safe) {
     HighHarm r;
     Counters cnt = {};
     r.alpha = 0.0;
     for (int m = 4; m <= max_harmonic; ++m) {
-        if ((double)m >= m_0) r.alpha += harmonic_alpha<0, COOP>(h, cnt, safe, m);
+        if ((double)m >= m_0) r.alpha += harmonic_alpha<0, LPR>(h, cnt, safe, m);
         else if (!(m_0 - (double)m > 0.02 * m_0)) safe = false;
     }
     r.n_harm = (int)cnt.n_harm; r.n_prune = (int)cnt.n_prune; r.safe = safe;
@@ -553,7 +593,7 @@ __device__ __noinline__ HighHarm harmonics_above_3(const HarmPre& h, int max_har
 // and m_0 = sqrt(1-N_par^2)/Y to move by 2 % over a distance far below the cell size of the spline tables.
 // HIGH: the instantiation that also sums harmonics 4..max_harmonic (kept out of the default kernels: even an
 // out-of-line call on a never-taken branch cost 6 % there, through the stack copy of HarmPre and its spills).
-template <bool HIGH, bool COOP = false>
+template <bool HIGH, int LPR = 1>
 __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, double Y, double iY, double N2, double N_par,
                                               double lnTe, Counters& cnt, bool& skip_ok) {
     skip_ok = false;
@@ -596,15 +636,15 @@ __device__ __forceinline__ double abs_albajar(const RayConst& rc, double X, doub
     double alpha = 0.0;
     bool safe = rc.alpha_floor > 0.0;
     if (rc.max_harmonic >= 2) {
-        if (2.0 >= m_0) alpha += harmonic_alpha<2, COOP>(h, cnt, safe);
+        if (2.0 >= m_0) alpha += harmonic_alpha<2, LPR>(h, cnt, safe);
         else if (!(m_0 - 2.0 > 0.02 * m_0)) safe = false;
     }
     if (rc.max_harmonic >= 3) {
-        if (3.0 >= m_0) alpha += harmonic_alpha<3, COOP>(h, cnt, safe);
+        if (3.0 >= m_0) alpha += harmonic_alpha<3, LPR>(h, cnt, safe);
         else if (!(m_0 - 3.0 > 0.02 * m_0)) safe = false;
     }
     if (HIGH && rc.max_harmonic >= 4) {
-        const HighHarm r = harmonics_above_3<COOP>(h, rc.max_harmonic, m_0, safe);
+        const HighHarm r = harmonics_above_3<LPR>(h, rc.max_harmonic, m_0, safe);
         alpha += r.alpha; cnt.n_harm += r.n_harm; cnt.n_prune += r.n_prune; safe = r.safe;
     }
     skip_ok = safe;
@@ -627,19 +667,20 @@ struct AlphaIn {
 // WITH_PSI: du[7] = psi_N at the point and du[8] = grad(psi_N) . dx/ds (inputs of the streaming deposition)
 // alpha_skip (in/out, optional): on entry true = take alpha = 0 without evaluating it (see abs_albajar); on exit, when
 // alpha was evaluated, whether the next step's inner stages may skip it.
-// COOP: the call is made by a full warp on ONE ray (warp-uniform arguments); the harmonic integrals are split over lanes.
+// LPR: lanes per ray. LPR > 1: the call is made by the LPR lanes of a group on ONE ray (uniform arguments); the harmonic
+// integrals are split over them.
 // ain (optional): filled for an absorption model the caller evaluates itself (then WITH_ALPHA = false, du[6] = 0).
-template <bool WITH_ALPHA, bool WITH_PSI = false, bool HIGH = false, bool COOP = false>
+template <bool WITH_ALPHA, bool WITH_PSI = false, bool HIGH = false, int LPR = 1>
 __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, const double* u, double* du, Counters& cnt,
                                     PointVals* pv = nullptr, bool skip_alpha = false, bool* skip_ok = nullptr,
-                                    AlphaIn* ain = nullptr) {
+                                    AlphaIn* ain = nullptr, bool need_psi = true) {
     const double x = u[0], y = u[1], z = u[2], Nx = u[3], Ny = u[4], Nz = u[5];
     const double R2 = fma(x, x, y * y);
     const double iR = rsqrt_fast(R2);
     const double R = R2 * iR;
     const double c = x * iR, s = y * iR;
     Fields f;
-    eval_fields<WITH_PSI>(T, R, z, f);
+    eval_fields<WITH_PSI>(T, R, z, f, need_psi);
     const double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
     const double iB = rsqrt_fast(B2);
     const double Babs = B2 * iB;
@@ -680,7 +721,7 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
             cnt.n_askip++;
         } else {
             bool ok;
-            const double alpha = abs_albajar<HIGH, COOP>(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
+            const double alpha = abs_albajar<HIGH, LPR>(rc, X, Y, iY, N2, Np, f.lnTe, cnt, ok);
             du[6] = -u[6] * alpha;
             if (skip_ok) *skip_ok = ok;
         }

@@ -274,6 +274,14 @@ struct TraceArgs {
     int* rays_left;                   // rays not yet retired
     const double2* warm_tab;          // [501] (t_i, exp(-t_i^2) dt): set_extv! tables of the warm-plasma model
     double* u_final;                  // [7][n] state of every ray at retirement, or NULL
+    // staged hand-off (the tail of a large bundle continues with several lanes per ray; torj_api.cu: trace stages):
+    // this launch stops before the first segment round that starts with <= stop_left rays alive and publishes that
+    // round in *stop_seg; the next launch takes its rounds from *first_seg and its rays from ray_list[0 .. *n_list)
+    int stop_left;                    // 0 = run to the end
+    int* stop_seg;                    // out (initialised to INT_MAX), or NULL
+    const int* first_seg;             // in, or NULL (= 0)
+    const int* ray_list;              // in: the rays still alive, ascending, or NULL (= all rays)
+    const int* n_list;                // in: length of ray_list
 };
 #define TORJ_HAND_D 20
 #define TORJ_SEG_RETIRED 0x7fffffff
@@ -332,13 +340,16 @@ enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT 
 // HIGH = true: harmonics above the third enabled (torj_options.max_harmonic > 3); see abs_albajar
 // MODEL: 0 = Albajar absorption (reference src/absorption.jl), 1 = warm-plasma damping (src/general_absorption.jl α,
 //   torj_warm.cuh): the RHS leaves alpha out and the warp evaluates it cooperatively right after.
-// COOP = true: a WARP per ray instead of a thread per ray (torj_options.lanes_per_ray = 32). All 32 lanes carry the same
-//   ray state and run the same bookkeeping (no divergence, nothing to broadcast); the parallel parts — the nodes of the
-//   harmonic integrals / of the warm quadrature — are split over the lanes and butterfly-reduced, so every lane sees
-//   bit-identical sums. Lane 0 alone performs the side effects (bins, per-ray outputs, queue bookkeeping). For bundles
-//   far below the resident lanes (37 888) and for the warm model, whose alpha costs ~100x the rest of the RHS.
-template <int SCH, bool HIGH = false, int MODEL = 0, bool COOP = false>
+// LPR: lanes per ray (torj_options.lanes_per_ray): 1 = a thread per ray; 8 / 32 = a group of 8 lanes / a whole warp per
+//   ray. All lanes of a group carry the same ray state and run the same bookkeeping (no divergence inside the group,
+//   nothing to broadcast); the parallel parts — the nodes of the harmonic integrals / of the warm quadrature — are split
+//   over the group and butterfly-reduced, so every lane of it sees bit-identical sums. The group's first lane alone
+//   performs the side effects (bins, per-ray outputs, queue bookkeeping). For bundles below the resident lanes
+//   (37 888), where the time is one ray's latency, for the tail of a large bundle (`resume`), and for the warm model,
+//   whose alpha costs ~100x the rest of the RHS.
+template <int SCH, bool HIGH = false, int MODEL = 0, int LPR = 1>
 __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
+    constexpr bool COOP = LPR == 32;
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
     extern __shared__ double smem[];
@@ -367,7 +378,11 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     const long long n = a.B.n_rays;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
-    const bool writer = !COOP || lane == 0;  // the lane that performs a ray's side effects
+    const bool writer = (lane & (unsigned)(LPR - 1)) == 0;  // the lane that performs a ray's side effects
+    const unsigned gmask = group_mask(LPR);                 // the lanes that hold my ray
+    const unsigned gleader = lane & ~(unsigned)(LPR - 1);
+    const unsigned leaders = LPR == 1 ? FULL : (LPR == 32 ? 1u : 0x01010101u);
+    static_assert(LPR == 1 || LPR == 8 || LPR == 32, "lanes per ray");
     const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
     // OrdinaryDiffEq's step_accept_controller! holds the step (q := 1) when qsteady_min = 1 <= q <= qsteady_max = 1.2.
@@ -520,8 +535,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     auto claim = [&](long long idx, bool aligned) {
         ray = idx;
         int d = atomicAdd(&a.seg_done[idx], 0);
-        if (COOP) d = __shfl_sync(FULL, d, 0);  // one observation for the whole warp (another SM may write in between)
-        if (d == TORJ_SEG_RETIRED) {
+        if (LPR > 1) d = __shfl_sync(gmask, d, gleader);  // one observation for the whole group (another SM may write in between)
+        if (d == TORJ_SEG_RETIRED || d > wseg) {  // retired, or this segment was done by an earlier stage (ragged cut)
             phase = PH_IDLE; ray = -1;
         } else if (d == wseg && aligned) {
             __threadfence();
@@ -541,6 +556,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         }
     };
 
+    // item space of this launch: rounds first_seg .. n_segments-1 over the rays of ray_list (default: all rounds, all rays)
+    const long long n_round = a.ray_list ? (long long)__ldg(a.n_list) : n;
+    const int seg0 = a.first_seg ? min(__ldg(a.first_seg), O.n_segments) : 0;
+    const long long n_items = n_round * (long long)(O.n_segments - seg0);
     for (;;) {
         // ---- warp-ballot retire-and-refill: idle lanes draw the next work items from the global queue.
         // With segment hand-off a segment starts only on every (S-1)-th trip of the warp: a step is S-1 trips, so the
@@ -555,15 +574,17 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         if (need) {
             int leader = __ffs(need) - 1;
             unsigned long long base = 0;
-            int left = 1;
+            int left = 1, stop = 0x7fffffff;
             if ((int)lane == leader) {
-                base = atomicAdd(a.next_ray, COOP ? 1ull : (unsigned long long)__popc(need));
+                base = atomicAdd(a.next_ray, (unsigned long long)__popc(need & leaders));
                 if (a.interleave) left = atomicAdd(a.rays_left, 0);
+                if (a.stop_seg) stop = *(volatile int*)a.stop_seg;
             }
             base = __shfl_sync(FULL, base, leader);
             left = __shfl_sync(FULL, left, leader);
+            stop = __shfl_sync(FULL, stop, leader);
             if (phase == PH_IDLE && !exhausted) {
-                long long idx = (long long)base + (COOP ? 0 : __popc(need & ((1u << lane) - 1u)));
+                long long idx = (long long)base + __popc(need & leaders & ((1u << gleader) - 1u));
                 if (!a.interleave) {
                     if (idx >= n) {
                         exhausted = true;
@@ -572,11 +593,19 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     }
                 } else {
                     // item idx = segment idx / n of ray idx % n; items of retired rays are void
-                    if (left == 0 || idx >= n * (long long)O.n_segments) {
+                    if (left == 0 || idx >= n_items) {
                         exhausted = true;
                     } else {
-                        wseg = (int)(idx / n);
-                        claim(idx - (long long)wseg * n, aligned);
+                        const int round = (int)(idx / n_round);
+                        wseg = seg0 + round;
+                        long long r = idx - (long long)round * n_round;
+                        if (a.ray_list) r = __ldg(a.ray_list + r);
+                        // few rays left: finish this round, leave the following ones to the next stage. Items are handed
+                        // out in order, so nothing of a later round has been drawn yet (but for the lanes of this very
+                        // draw: a ragged cut, which claim() of the next stage tolerates)
+                        if (a.stop_seg && left <= a.stop_left && wseg + 1 < stop && writer) atomicMin(a.stop_seg, wseg + 1);
+                        if (wseg >= stop) exhausted = true;
+                        else claim(r, aligned);
                     }
                 }
             }
@@ -591,7 +620,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         if (MODEL == 0) {
             if (phase >= PH_SEED) {
                 const bool inner = (phase == PH_STAGE && st < S - 1);
-                rhs<true, true, HIGH, COOP>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next);
+                rhs<true, true, HIGH, LPR>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next, nullptr,
+                                            !inner && phase != PH_INITDT);  // psi_N is used at the FSAL / seed / callback stages only
                 if (!inner) a_skip = a_skip_next;
             }
         } else {
@@ -600,7 +630,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             ain.X = 0.1; ain.Y = 0.5; ain.N2 = 1.0; ain.Np = 0.0; ain.lnTe = -1e300; ain.inorm = 1.0;
             const bool evaluated = phase >= PH_SEED;
             const bool inner = (phase == PH_STAGE && st < S - 1);
-            if (evaluated) rhs<false, true, false, false>(T, rc, tmp, out, cnt, nullptr, false, nullptr, &ain);
+            if (evaluated) rhs<false, true, false, false>(T, rc, tmp, out, cnt, nullptr, false, nullptr, &ain, !inner && phase != PH_INITDT);
             const bool want = evaluated && !(inner && a_skip);
             if (evaluated && !want) cnt.n_askip++;
             const double alpha = warm_alpha_warp<COOP>(a.warm_tab, rc, ain, want, wstash, TORJ_TPB, cnt, a_skip_next);
@@ -827,7 +857,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
     // ---- block reduction: warp shuffles, shared-memory atomics, then global atomics
     unsigned long long c6[8] = {cnt.n_acc, cnt.n_rej, cnt.n_rhs, cnt.n_alpha, cnt.n_harm, rays_ok, cnt.n_prune, cnt.n_askip};
-    if (!writer) {  // COOP: the other 31 lanes carry copies of lane 0's counts
+    if (!writer) {  // LPR > 1: the other lanes of a group carry copies of its first lane's counts
 #pragma unroll
         for (int q = 0; q < 8; ++q) c6[q] = 0ull;
     }
@@ -854,6 +884,29 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #undef PK
 #undef PKI
 #endif
+}
+
+// Rays not yet retired, ascending (one block: the order keeps neighbouring rays on neighbouring lanes): input of a tail stage
+__global__ void k_compact_live(const int* __restrict__ seg_done, long long n, int* __restrict__ list, int* __restrict__ n_list) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (long long start = 0; start < n; start += blockDim.x) {
+        const long long i = start + threadIdx.x;
+        const bool live = i < n && seg_done[i] != TORJ_SEG_RETIRED;
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_warp[w] = __popc(b);
+        __syncthreads();
+        int off = 0, total = 0;
+        for (int q = 0; q < nw; ++q) { const int c = s_warp[q]; if (q < w) off += c; total += c; }
+        if (live) list[s_base + off + __popc(b & ((1u << lane) - 1u))] = (int)i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_list = s_base;
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
