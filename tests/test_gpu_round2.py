@@ -117,14 +117,17 @@ def test_warm_single_ray_against_oracle(gl24, launcher, lanes):
     psi = np.linspace(0.0, 1.0, 300)
     opt = tj.default_options(absorption_model=1, alpha_floor=0.0, lanes_per_ray=lanes)
     s, u, P, prof, dep = tj.make_ray(pl, launcher["x0"], launcher["N0"], 95e9, 1, 0.35, psi, options=opt)
-    ro = opl.make_ray(launcher["x0"], launcher["N0"], 95e9, 1, 0.35, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
+    # like for like: the ray is cut at s_max inside the plasma, where the reference's root pairing and the streaming deposition
+    # treat the last, open shell differently (the beam test below runs its rays to the end and uses the reference's algorithm)
+    ro = opl.make_ray(launcher["x0"], launcher["N0"], 95e9, 1, 0.35, psi, gl24, opts=O.OracleOptions.default(absorption_model=1),
+                      deposition="streaming")
     assert ro["status"] == 0 and len(s) == len(ro["s"])
     xyz = np.array(u)
     assert max(np.abs(xyz[:, 0] - ro["x"]).max(), np.abs(xyz[:, 1] - ro["y"]).max(), np.abs(xyz[:, 2] - ro["z"]).max()) < TRAJ_TOL
     assert np.abs(P - ro["P"]).max() < 1e-8
     assert 0.05 < ro["deposited_power"]
     assert abs(dep - ro["deposited_power"]) <= FRAC_TOL * ro["deposited_power"]
-    assert l2rel(prof, ro["dP_dV"]) < L2_FAITHFUL
+    assert l2rel(prof, ro["dP_dV"]) < 1e-6
 
 
 def test_warm_beam_gate_and_mappings_agree(gl24, launcher):

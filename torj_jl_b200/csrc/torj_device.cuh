@@ -32,7 +32,8 @@ namespace torj {
 #define TORJ_PAIR 1      // harmonic integrals over node PAIRS (+t, -t): the Bessel series of a pair are evaluated once
 #endif
 #ifndef TORJ_PSI_LAZY
-#define TORJ_PSI_LAZY 1  // psi_N rides on the stencil only at the stages whose psi is used (FSAL / seed / callback)
+#define TORJ_PSI_LAZY 0  // 1: psi_N rides on the stencil only at the stages whose psi is used. Measured SLOWER (134.6 -> 141.0 ms: the
+                         // predicate costs more than the 37 DFMA it saves); kept for the record, off
 #endif
 
 struct DevTables {
