@@ -534,6 +534,15 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     // try to start the held item (ray idx, segment wseg): possible once the ray's previous segment has been handed in
     auto claim = [&](long long idx, bool aligned) {
         ray = idx;
+        if (a.stop_seg) {
+            // Staged run: an item of a round at or beyond the stop round is left to the next stage — also one that was drawn
+            // before the flag was set and is still waiting here. (Without this a waiting item could outlive its
+            // predecessor's being dropped by a lane that saw the flag earlier: the two reads of the flag are not ordered
+            // with the queue's atomicAdd.) Items already running finish their segment: a ragged cut the next stage tolerates.
+            int sv = *(volatile int*)a.stop_seg;
+            if (LPR > 1) sv = __shfl_sync(gmask, sv, gleader);
+            if (wseg >= sv) { phase = PH_IDLE; ray = -1; exhausted = true; return; }
+        }
         int d = atomicAdd(&a.seg_done[idx], 0);
         if (LPR > 1) d = __shfl_sync(gmask, d, gleader);  // one observation for the whole group (another SM may write in between)
         if (d == TORJ_SEG_RETIRED || d > wseg) {  // retired, or this segment was done by an earlier stage (ragged cut)
