@@ -31,6 +31,9 @@ namespace torj {
 #ifndef TORJ_PAIR
 #define TORJ_PAIR 1      // harmonic integrals over node PAIRS (+t, -t): the Bessel series of a pair are evaluated once
 #endif
+#ifndef TORJ_PAIR_EXP
+#define TORJ_PAIR_EXP 1  // the two exponentials of a node pair from ONE exp and one reciprocal (see harmonic_sum)
+#endif
 #ifndef TORJ_PSI_LAZY
 #define TORJ_PSI_LAZY 0  // 1: psi_N rides on the stencil only at the stages whose psi is used. Measured SLOWER (134.6 -> 141.0 ms: the
                          // predicate costs more than the 37 DFMA it saves); kept for the record, off
@@ -432,6 +435,7 @@ struct HarmPre {  // per-call invariants of the harmonic integral
 
 struct HarmCoef {  // per-harmonic invariants
     double x_m, e0, e1, k1, k2, k3m2, k3, k4, k5, k6, scale;
+    double eb, c2, ae1;  // exp(e0 + |e1|) (the largest exponential on the resonance curve), exp(-2 |e1|), |e1|
 };
 
 // reference src/absorption.jl:132-189: sum over the Gauss-Legendre nodes for harmonic M
@@ -453,7 +457,16 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
     for (int k = (int)(threadIdx.x & (unsigned)(LPR - 1)); k < half; k += LPR) {
         const double t = c_gl.t[k], sq = c_gl.sq[k];
         const double et = c.e1 * t;
+#if TORJ_PAIR_EXP
+        // exp(e0 +- et) = eb * exp(+-et - |e1|): the larger factor from one exp, the smaller one as exp(-2|e1|) / larger.
+        // (c2 = 0 when it would underflow: the smaller term is then < 1e-150 of the larger one.)
+        const double big = exp_fast(fabs(et) - c.ae1);
+        const double small = c.c2 * rcp_fast(big);
+        const bool pos = et >= 0.0;
+        const double exa = c.eb * (pos ? big : small), exb = c.eb * (pos ? small : big);
+#else
         const double exa = exp_fast(c.e0 + et), exb = exp_fast(c.e0 - et);
+#endif
         const double z = c.x_m * sq;
         double J, D;
         if (GENERIC) {
@@ -546,13 +559,15 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     // (m/(N_perp omega_bar))^2 * c_abs_m * sqrt((m/m0)^2-1) and the conversion to alpha (reference
     // src/absorption.jl:165,186,218-223); the reference's overall minus sign cancels the (-mu) of the integrand
     c.scale = h.pref * (fm * fm * h.Y * h.Y * h.iNp2) * q * h.to_alpha;
+    c.ae1 = fabs(c.e1);
+    const double emax = c.e0 + c.ae1;
+    c.eb = exp_fast(emax);
     if (h.floor_ > 0.0) {
         // |J_n| <= 1, |D| = |z (J_{m-1} - J_{m+1})/2| <= x_m, sum of weights = 2, exponent <= e0 + |e1|
         const double xm = c.x_m;
         const double pmax = fabs(c.k1) + fabs(c.k2) * xm + fabs(c.k3m2) + fabs(c.k3) * xm * xm + fabs(c.k4) + fabs(c.k5)
                             + fabs(c.k6) * xm;
-        const double emax = c.e0 + fabs(c.e1);
-        const double bound = 2.0 * pmax * fabs(c.scale) * exp_fast(emax < 0.0 ? emax : 0.0);
+        const double bound = 2.0 * pmax * fabs(c.scale) * (emax < 0.0 ? c.eb : 1.0);
         if (bound < h.floor_) {
             cnt.n_prune++;
             if (!(bound < h.floor_ * TORJ_SKIP_MARGIN)) safe = false;
@@ -561,6 +576,9 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     }
     safe = false;
     cnt.n_harm++;
+#if TORJ_PAIR_EXP && TORJ_PAIR
+    c.c2 = c.ae1 > 350.0 ? 0.0 : exp_fast(-2.0 * c.ae1);
+#endif
     if (M == 0 && m > 3) return harmonic_sum<2, 1, true, LPR>(c, m);
     if (c.x_m <= 3.2) return harmonic_sum<M, 12, false, LPR>(c, m);
     return harmonic_sum_large<M, LPR>(c, m);

@@ -317,6 +317,9 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #define TORJ_PARK 1  // 1: per-segment / per-ray scalars of the integrator live in shared memory
 #endif
 #define TORJ_PARK_SLOTS 9  // doubles per thread reserved when TORJ_PARK (7 doubles + 3 ints, rounded up)
+#ifndef TORJ_ROLL_J
+#define TORJ_ROLL_J 0  // 1: the stage-combination and error-estimate sums run as real loops over the stages (smaller hot code)
+#endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
@@ -688,7 +691,11 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
                 // stale slots hold finite values of the previous step, so the trip count is lane-independent
                 double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#if TORJ_ROLL_J
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
                 for (int j = 0; j < S - 1; ++j) {
                     const double aj = s_a[st][j];
 #pragma unroll
@@ -703,11 +710,24 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 dpsi_new = out[8];
                 double at[7];
                 bool bad = false;
+#if TORJ_ROLL_J
+                double utv[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+                for (int j = 0; j < S; ++j) {
+                    const double bj = s_bt[j];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) utv[i] = fma(bj, KK(j, i), utv[i]);
+                }
+#endif
 #pragma unroll
                 for (int i = 0; i < 7; ++i) {
+#if TORJ_ROLL_J
+                    double ut = utv[i];
+#else
                     double ut = 0.0;
 #pragma unroll
                     for (int j = 0; j < S; ++j) ut = fma(s_bt[j], KK(j, i), ut);
+#endif
                     ut *= dt;
                     const double au = fabs(u[i]), an = fabs(tmp[i]);
                     at[i] = ut * rcp_fast(O.abstol + (au > an ? au : an) * O.reltol);
