@@ -68,9 +68,11 @@ typedef struct torj_options {
                                       2 = segment hand-off: a ray may change lanes between two of its n_segments
                                       segments, so all rays advance together: no partly filled last wave, and the lanes
                                       of a warp stay in step (automatic picks this when the bundle exceeds the resident
-                                      lanes, 37 888 on a B200). With one lane per ray the tail of such a run — fewer rays
-                                      alive than lanes — continues in stages with 8 and then 32 lanes per ray;
-                                      3 = segment hand-off without those tail stages */
+                                      lanes, 37 888 on a B200). With the Albajar model the rounds of the hand-off are
+                                      life-ordered: a pilot march (straight line, real fields and alpha, one point per
+                                      segment) predicts every ray's life and the long-lived rays start first, so that all
+                                      rays end together instead of the longest ones finishing alone;
+                                      3 = plain segment hand-off: every ray starts in round 0 */
     int32_t absorption_model;      /* 0 = Albajar (reference src/absorption.jl:191-235, what the reference's gradΛ! calls);
                                       1 = warm-plasma damping: alpha = α(ω, X, Y, |N|, acos(N∥/|N|), Te, v_g_perp, mode)[2] of
                                       reference src/general_absorption.jl:1328-1337 (iwarm = 3, Larmor order lrm <= 5) in the

@@ -15,7 +15,7 @@ pa, da, wa = bench.sweep_bundle()
 out = {}
 for world in (16, 8, 4, 2, 1):
     idx = shard_block_cyclic(len(wa), 1025, 0, world)
-    for sch in (3, 0):
+    for sch in (3, 0):  # 3 plain hand-off, 0 life-ordered rounds
         ms = []
         for rep in range(3 if world > 1 else 2):
             r = tj.trace_bundle(pl, pa[idx], da[idx], wa[idx], 95e9, 1, 1.0, PSI, options=tj.default_options(schedule=sch, lanes_per_ray=1))

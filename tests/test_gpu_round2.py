@@ -198,10 +198,10 @@ def test_warp_per_ray_high_harmonics_and_exact_mode(gl24, launcher):
     assert res["counters"] == one["counters"] and np.abs(res["P_final"] - one["P_final"]).max() < 1e-12
 
 
-def test_tail_stages_agree_with_plain_handoff(gpu_full, oracle_full, gl24, launcher):
-    """65 543 rays > 37 888 resident lanes: segment hand-off; when few rays are left the launch stops, the survivors are
-    compacted and continue from their hand-off records with 8 lanes per ray, then a warp per ray (schedule 0 / 2). Same rays as
-    the plain hand-off (schedule 3) up to the summation order of the node sums in the tail."""
+def test_life_ordered_rounds_give_the_same_rays(gpu_full, oracle_full, gl24, launcher):
+    """65 543 rays > 37 888 resident lanes: segment hand-off. Default: a pilot march predicts every ray's life, the rounds are
+    shifted so that all rays end together, and a lane whose successor item was drawn early keeps its ray (continuation).
+    Scheduling only: per-ray results are IDENTICAL to the plain hand-off (schedule 3) and to whole rays per lane (1)."""
     L = tj.lib()
     ctx = _lib.context()
     pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
@@ -209,18 +209,28 @@ def test_tail_stages_agree_with_plain_handoff(gpu_full, oracle_full, gl24, launc
     n0 = L.torj_ctx_launch_count(ctx)
     plain = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(schedule=3, lanes_per_ray=1))
     n1 = L.torj_ctx_launch_count(ctx)
-    staged = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(lanes_per_ray=1))
+    ordered = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(lanes_per_ray=1))
     n2 = L.torj_ctx_launch_count(ctx)
-    assert n1 - n0 == 3 and n2 - n1 == 7        # init, trace, finalize / init, 3 trace stages, 2 compactions, finalize
-    assert (staged["status"] == 0).all() and np.array_equal(plain["n_points"], staged["n_points"])
-    assert plain["counters"]["n_acc"] == staged["counters"]["n_acc"] and plain["counters"]["n_rhs"] == staged["counters"]["n_rhs"]
-    assert staged["counters"]["n_rays_ok"] == len(w)
-    assert np.abs(plain["P_final"] - staged["P_final"]).max() < 1e-12
-    assert np.abs(plain["P_deposited_ray"] - staged["P_deposited_ray"]).max() < 1e-11
-    assert abs(plain["deposited_power"] - staged["deposited_power"]) < 1e-12 and l2rel(staged["dP_dV"], plain["dP_dV"]) < 1e-11
+    whole = tj.trace_bundle(gpu_full, pos, dirs, w, launcher["f"], 1, 1.0, PSI, options=tj.default_options(schedule=1, lanes_per_ray=1))
+    assert n1 - n0 == 3 and n2 - n1 == 4        # init, trace, finalize / init, pilot march, trace, finalize
+    for r in (ordered, whole):
+        assert (r["status"] == 0).all() and np.array_equal(plain["n_points"], r["n_points"])
+        assert plain["counters"]["n_acc"] == r["counters"]["n_acc"] and plain["counters"]["n_rhs"] == r["counters"]["n_rhs"]
+        assert r["counters"]["n_rays_ok"] == len(w)
+        assert np.array_equal(plain["P_final"], r["P_final"]) and np.array_equal(plain["P_deposited_ray"], r["P_deposited_ray"])
+        assert abs(plain["deposited_power"] - r["deposited_power"]) < 1e-12 and l2rel(r["dP_dV"], plain["dP_dV"]) < 1e-12
     pick = np.linspace(0, len(w) - 1, 64).astype(int)
     ref = oracle_full.trace_bundle(pos[pick], dirs[pick], w[pick], launcher["f"], 1, 1.0, PSI, gl24, deposition="streaming")
-    assert np.array_equal(staged["n_points"][pick], ref["n_points"]) and np.abs(staged["P_final"][pick] - ref["P_final"]).max() < 1e-12
+    assert np.array_equal(ordered["n_points"][pick], ref["n_points"]) and np.abs(ordered["P_final"][pick] - ref["P_final"]).max() < 1e-12
+    # rays of very different lives in one bundle (two frequencies, failing rays, a trajectory window): still the same rays
+    n = 40000
+    f = np.where(np.arange(n) % 3 == 0, 110e9, 95e9)
+    p2 = pos[:n].copy(); p2[5] = [9.0, 0.0, 0.0]
+    a = tj.trace_bundle(gpu_full, p2, dirs[:n], w[:n], f, 1, 1.0, PSI, options=tj.default_options(schedule=3, lanes_per_ray=1), trajectories=(7, 3))
+    b = tj.trace_bundle(gpu_full, p2, dirs[:n], w[:n], f, 1, 1.0, PSI, options=tj.default_options(schedule=2, lanes_per_ray=1), trajectories=(7, 3))
+    assert a["status"][5] == 2 and np.array_equal(a["status"], b["status"]) and np.array_equal(a["n_points"], b["n_points"])
+    assert np.array_equal(a["P_final"], b["P_final"]) and np.array_equal(a["traj_xyz"], b["traj_xyz"]) and np.array_equal(a["traj_P"], b["traj_P"])
+    assert len(np.unique(a["n_points"])) > 3
 
 
 def test_eight_lanes_per_ray(gpu_small, oracle_small, gl24, launcher):

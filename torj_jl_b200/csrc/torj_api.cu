@@ -93,7 +93,7 @@ struct torj_bundle {
     double* d_hand = nullptr;
     int *d_segdone = nullptr, *d_left = nullptr;
     int h_left = 0;  // source of the copy into d_left (outlives the call)
-    int *d_stage = nullptr, *d_list = nullptr;  // tail stages: [2 stages][stop_seg, n_list], list of live rays
+    int *d_life = nullptr;                      // [n + 1]: predicted life of every ray in segments, then the maximum
     // trajectory window
     int64_t traj_first = 0, traj_count = 0;
     int traj_max = 0;
@@ -133,6 +133,9 @@ struct Guard {
 
 static int set_device(const torj_ctx* c) {
     CK(cudaSetDevice(c->device));
+    // Start every entry point from a clean error state: cudaGetLastError() after a kernel launch must report that launch,
+    // not a non-sticky error some earlier, unrelated runtime call of this host thread (ours or the application's) left behind.
+    (void)cudaGetLastError();
     return 0;
 }
 
@@ -818,7 +821,7 @@ void torj_bundle_destroy(torj_bundle* b) {
     cudaStreamSynchronize(b->ctx->stream);
     cudaFree(b->d_pos); cudaFree(b->d_dir); cudaFree(b->d_w); cudaFree(b->d_freq); cudaFree(b->d_mode); cudaFree(b->d_u0);
     cudaFree(b->d_s0); cudaFree(b->d_psil); cudaFree(b->d_Pf); cudaFree(b->d_Pdep); cudaFree(b->d_status); cudaFree(b->d_npts);
-    cudaFree(b->d_hand); cudaFree(b->d_segdone); cudaFree(b->d_left); cudaFree(b->d_stage); cudaFree(b->d_list);
+    cudaFree(b->d_hand); cudaFree(b->d_segdone); cudaFree(b->d_left); cudaFree(b->d_life);
     cudaFree(b->d_queue); cudaFree(b->d_counters); cudaFree(b->d_edges); cudaFree(b->d_bins); cudaFree(b->d_dV);
     cudaFree(b->d_profile);
     cudaFree(b->d_beam);
@@ -870,7 +873,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     torj_options_default(&od);
     if (opt) od = *opt;
     if (od.scheme != 0 && od.scheme != 1) FAIL("torj_bundle_trace: scheme must be 0 (Tsit5) or 1 (OwrenZen3)");
-    if (od.n_segments < 1) FAIL("torj_bundle_trace: n_segments < 1");
+    if (od.n_segments < 1 || od.n_segments > 16000) FAIL("torj_bundle_trace: n_segments must be in 1..16000");
     if (!(od.alpha_floor >= 0.0)) FAIL("torj_bundle_trace: alpha_floor must be >= 0");
     if (od.max_harmonic < 1 || od.max_harmonic > 16) FAIL("torj_bundle_trace: max_harmonic must be in 1..16 (1 = no absorption)");
     if (!(od.dtmax > 0.0) || !(od.abstol > 0.0) || !(od.reltol > 0.0)) FAIL("torj_bundle_trace: dtmax, abstol and reltol must be > 0");
@@ -933,15 +936,16 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.warm_tab = c->d_warm_tab; a.u_final = b->d_ufinal;
     const int model = od.absorption_model;
     // Several lanes per ray when the bundle cannot fill the GPU with one thread per ray — then the time is one ray's
-    // latency, and splitting the quadrature nodes over the lanes of a group shortens exactly that: a warp per ray up to
-    // the resident warps (1 184), 8 lanes per ray up to an eighth of the resident lanes (4 736). Measured (profiles/):
-    // a cold 1 025-ray beam 56 -> 61 ms (nothing to split), a 10 keV 1 025-ray beam 510 -> 170 ms. The warm model, whose
-    // alpha is ~100x the rest of the RHS and warp-cooperative either way, takes a warp per ray up to half the lanes.
+    // latency, and splitting the quadrature nodes over the lanes of a group shortens exactly that. Measured on 1 025 /
+    // 4 100-ray bundles (profiles/): cold 4 keV beam 54 (1 lane) / 52 (8) / 61 ms (32); 10 keV scan 282 / 220-239 / 170 ms
+    // per wave — but 32 lanes per ray fit only 1 184 rays at a time (4 100 rays: 600 ms). 8 lanes per ray up to an eighth
+    // of the resident lanes (4 736 rays) is never worse than one lane and close to the best everywhere. The warm model,
+    // whose alpha is ~100x the rest of the RHS and warp-cooperative either way, takes a warp per ray up to half the lanes.
     const int64_t lanes_guess = (int64_t)c->num_sms * TORJ_MINB * TORJ_TPB;
     int lpr = od.lanes_per_ray;
     if (lpr == 0) {
         if (model == 1) lpr = (b->n <= lanes_guess / 2) ? 32 : 1;
-        else lpr = (b->n * 32 <= lanes_guess) ? 32 : ((b->n * 8 <= lanes_guess) ? 8 : 1);
+        else lpr = (b->n * 8 <= lanes_guess) ? 8 : 1;
     }
     size_t smem = (size_t)n_psi * sizeof(double);
     if (model == 1 && lpr == 1) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
@@ -980,49 +984,23 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         CK(cudaMemcpyAsync(b->d_left, &b->h_left, sizeof(int), cudaMemcpyHostToDevice, st));
         a.hand = b->d_hand; a.seg_done = b->d_segdone; a.rays_left = b->d_left;
     }
-    a.stop_left = 0; a.stop_seg = nullptr; a.first_seg = nullptr; a.ray_list = nullptr; a.n_list = nullptr;
-    // Tail stages (hand-off schedule, Albajar model, one lane per ray): when fewer rays are alive than lanes, the rays that
-    // are left — the longest ones, deep in the absorbing layer — run alone on their lanes while the rest of the GPU idles.
-    // The launch therefore stops at the segment round that begins with few rays alive; the survivors are compacted and
-    // continue from their hand-off records with 8 lanes per ray, the last ones with a warp per ray (torj_kernels.cuh).
-    const bool staged = interleave && lpr == 1 && model == 0 && od.schedule != 3;
+    a.life = nullptr; a.lmax = nullptr;
     CK(cudaEventRecord(c->ev0, st));
-    if (!staged) {
-        kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+    // Life-ordered rounds (hand-off schedule, Albajar model): breadth-first rounds make all rays advance together, so the
+    // few longest-lived rays finish alone while the GPU idles — a fixed ~67 ms on the 1 M-ray sweep whatever the number of
+    // GPUs (profiles/). A pilot march predicts every ray's life; the rounds are shifted so that all rays END together and
+    // the long ones start first, while idle lanes run ahead in the queue and start the short ones early.
+    if (interleave && model == 0 && od.schedule != 3) {
+        if (!b->d_life) CK(cudaMalloc(&b->d_life, ((size_t)b->n + 1) * sizeof(int)));
+        CK(cudaMemsetAsync(b->d_life + b->n, 0, sizeof(int), st));
+        k_predict_life<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so, b->d_life, b->d_life + b->n);
         c->launches++;
         CK(cudaGetLastError());
-    } else {
-        if (!b->d_stage) CK(cudaMalloc(&b->d_stage, 4 * sizeof(int)));
-        if (!b->d_list) CK(cudaMalloc(&b->d_list, (size_t)b->n * sizeof(int)));
-        static const int h_init[4] = {0x7fffffff, 0, 0x7fffffff, 0};
-        CK(cudaMemcpyAsync(b->d_stage, h_init, sizeof h_init, cudaMemcpyHostToDevice, st));
-        const int lprs[3] = {1, 8, 32};
-        for (int sgi = 0; sgi < 3; ++sgi) {
-            trace_kernel_t ks = pick_trace_kernel(od.scheme, high, model, lprs[sgi]);
-            int bs = 0;
-            CK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bs, ks, TORJ_TPB, smem));
-            if (bs < 1) FAIL("torj_bundle_trace: trace kernel does not fit on an SM (n_psi too large for shared memory)");
-            const int64_t cap = (int64_t)c->num_sms * bs * TORJ_TPB;  // lanes
-            TraceArgs as = a;
-            if (sgi > 0) {  // rounds and rays of this stage: where the previous one stopped
-                k_compact_live<<<1, 1024, 0, st>>>(b->d_segdone, (long long)b->n, b->d_list, b->d_stage + 2 * (sgi - 1) + 1);
-                c->launches++;
-                CK(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), st));
-                as.first_seg = b->d_stage + 2 * (sgi - 1);
-                as.ray_list = b->d_list;
-                as.n_list = b->d_stage + 2 * (sgi - 1) + 1;
-            }
-            if (sgi < 2) {  // stop when the rays left fit the next stage's mapping (8 lanes per ray gains ~2.5x per ray: two waves)
-                as.stop_seg = b->d_stage + 2 * sgi;
-                as.stop_left = (int)std::min<int64_t>(sgi == 0 ? 2 * cap / 8 : cap / 32, 0x7fffffff);
-            }
-            const int64_t gs = sgi == 0 ? grid : (int64_t)c->num_sms * bs;
-            ks<<<(unsigned)gs, TORJ_TPB, smem, st>>>(as);
-            c->launches++;
-            CK(cudaGetLastError());
-        }
+        a.life = b->d_life; a.lmax = b->d_life + b->n;
     }
+    kern<<<(unsigned)grid, TORJ_TPB, smem, st>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, st));
     c->ev_valid = true;
     k_finalize<<<(unsigned)(((size_t)b->n_beams * (n_psi + 2) + 127) / 128), 128, 0, st>>>(b->d_bins, b->d_dV, n_psi, b->n_beams,

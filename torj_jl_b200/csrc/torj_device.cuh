@@ -32,7 +32,11 @@ namespace torj {
 #define TORJ_PAIR 1      // harmonic integrals over node PAIRS (+t, -t): the Bessel series of a pair are evaluated once
 #endif
 #ifndef TORJ_PAIR_EXP
-#define TORJ_PAIR_EXP 1  // the two exponentials of a node pair from ONE exp and one reciprocal (see harmonic_sum)
+#define TORJ_PAIR_EXP 0  // 1: the two exponentials of a node pair from ONE exp and one reciprocal (see harmonic_sum). Measured
+                         // slower on the headline bundle (129.7 -> 132.0 ms: longer dependent chain per pair); kept for the record, off
+#endif
+#ifndef TORJ_ROLL_DEPO
+#define TORJ_ROLL_DEPO 0  // 1: the three Newton steps of a level crossing as a real loop (smaller hot code)
 #endif
 #ifndef TORJ_PSI_LAZY
 #define TORJ_PSI_LAZY 0  // 1: psi_N rides on the stencil only at the stages whose psi is used. Measured SLOWER (134.6 -> 141.0 ms: the
@@ -561,7 +565,8 @@ __device__ __forceinline__ double harmonic_alpha(const HarmPre& h, Counters& cnt
     c.scale = h.pref * (fm * fm * h.Y * h.Y * h.iNp2) * q * h.to_alpha;
     c.ae1 = fabs(c.e1);
     const double emax = c.e0 + c.ae1;
-    c.eb = exp_fast(emax);
+    c.eb = 1.0; c.c2 = 0.0;
+    if (TORJ_PAIR_EXP || h.floor_ > 0.0) c.eb = exp_fast(emax);
     if (h.floor_ > 0.0) {
         // |J_n| <= 1, |D| = |z (J_{m-1} - J_{m+1})/2| <= x_m, sum of weights = 2, exponent <= e0 + |e1|
         const double xm = c.x_m;
@@ -801,7 +806,11 @@ __device__ __forceinline__ void depo_step(DepoState& st, const double* __restric
         }
         double gl = __ldg(g + lvl);
         double th = (gl - psi_a) / (psi_b - psi_a);
+#if TORJ_ROLL_DEPO
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int it = 0; it < 3; ++it) {
             double f = hermite(psi_a, psi_b, dpsi_a, dpsi_b, h, th) - gl;
             double d = hermite_d(psi_a, psi_b, dpsi_a, dpsi_b, h, th);

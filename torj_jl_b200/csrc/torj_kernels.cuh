@@ -270,21 +270,21 @@ struct TraceArgs {
     // segments, so all rays advance together and the bundle ends after n/lanes ray-times instead of ceil(n/lanes)
     int interleave;
     double* hand;                     // [n][TORJ_HAND_D] ray state between two segments
-    int* seg_done;                    // [n] segments completed; TORJ_SEG_RETIRED once the ray has ended
+    int* seg_done;                    // [n] bits 0-14: segments completed, bits 15-29: 1 + the highest segment whose work item
+                                      // was drawn before it could start and therefore dropped (its holder continues
+                                      // instead); TORJ_SEG_RETIRED once the ray has ended
     int* rays_left;                   // rays not yet retired
     const double2* warm_tab;          // [501] (t_i, exp(-t_i^2) dt): set_extv! tables of the warm-plasma model
     double* u_final;                  // [7][n] state of every ray at retirement, or NULL
-    // staged hand-off (the tail of a large bundle continues with several lanes per ray; torj_api.cu: trace stages):
-    // this launch stops before the first segment round that starts with <= stop_left rays alive and publishes that
-    // round in *stop_seg; the next launch takes its rounds from *first_seg and its rays from ray_list[0 .. *n_list)
-    int stop_left;                    // 0 = run to the end
-    int* stop_seg;                    // out (initialised to INT_MAX), or NULL
-    const int* first_seg;             // in, or NULL (= 0)
-    const int* ray_list;              // in: the rays still alive, ascending, or NULL (= all rays)
-    const int* n_list;                // in: length of ray_list
+    // life-ordered rounds (k_predict_life): ray r's segment k is item (round k + lmax - life[r], r), so that long-lived rays
+    // start first and all rays END together — no tail of a few long rays running alone. NULL = every ray starts in round 0
+    const int* life;                  // [n] predicted number of segments of every ray, 1 .. n_segments
+    const int* lmax;                  // max of life[]
 };
 #define TORJ_HAND_D 20
 #define TORJ_SEG_RETIRED 0x7fffffff
+#define TORJ_SEG_DONE(w) ((w) & 0x7fff)
+#define TORJ_SEG_DROP(w) (((w) >> 15) & 0x7fff)
 
 __device__ __forceinline__ double eps_of(double x) {  // Julia eps(x)
     x = fabs(x);
@@ -318,7 +318,8 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #endif
 #define TORJ_PARK_SLOTS 9  // doubles per thread reserved when TORJ_PARK (7 doubles + 3 ints, rounded up)
 #ifndef TORJ_ROLL_J
-#define TORJ_ROLL_J 0  // 1: the stage-combination and error-estimate sums run as real loops over the stages (smaller hot code)
+#define TORJ_ROLL_J 1  // 1: the stage-combination and error-estimate sums run as real loops over the stages: 170 hot instructions
+                       // less against a 32 KB instruction cache (measured 132.0 -> 126.7 ms); 0 = fully unrolled
 #endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
@@ -435,6 +436,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     int npts = 0, rstat = 0, nstep = 0;
     bool a_skip = false, a_skip_next = false;
     int wseg = 0;  // segment index of the work item held (segment hand-off)
+    bool own = false;  // PH_WAIT: the ray's state is already in this lane's registers (continuation), nothing to load
     int cadence = 0;  // trip number modulo the trips per step (warp-uniform)
     RayConst rc = make_ray_const(1e11, 1, O.te_min, O.max_harmonic, O.alpha_floor);
     DepoState dst = {0, 0, 1.0};
@@ -511,7 +513,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         __stcg(h + 8, make_double2(dst.P_last, pdep));
         __stcg(h + 9, make_double2(__hiloint2double(dst.shell, dst.valid), __hiloint2double(npts, rstat | (a_skip ? 256 : 0))));
         __threadfence();
-        atomicExch(&a.seg_done[ray], seg);
     };
     auto load_ray = [&](long long idx) {
         bind_ray(idx);
@@ -534,44 +535,55 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         seg = wseg;
         phase = PH_RESUME;
     };
-    // try to start the held item (ray idx, segment wseg): possible once the ray's previous segment has been handed in
+    // the held item (ray idx, segment wseg) is ready: take the ray over
+    auto start_item = [&](long long idx) {
+        __threadfence();
+        if (wseg > 0) {
+            load_ray(idx);
+        } else if (a.B.status[idx] == 0) {
+            start_ray(idx);
+        } else {  // failed initialisation (k_ray_init): retire at once
+            if (writer) {
+                atomicExch(&a.seg_done[idx], TORJ_SEG_RETIRED);
+                atomicSub(a.rays_left, 1);
+            }
+            phase = PH_IDLE; ray = -1;
+        }
+    };
+    // A freshly drawn item (ray idx, segment wseg). Nobody ever waits for an unfinished predecessor: if the ray's previous
+    // segment is still running, the item is DROPPED and marked as such in the ray's word, and the lane that runs that segment
+    // finds the mark when it hands in and continues with the ray itself (ACT_END_SEGMENT). Both sides use one atomic on
+    // the same word, so exactly one of them runs the segment. (Idle lanes that ran ahead in the queue used to hold such
+    // items and block; with life-ordered rounds that would idle most lanes while the long rays start.)
     auto claim = [&](long long idx, bool aligned) {
         ray = idx;
-        if (a.stop_seg) {
-            // Staged run: an item of a round at or beyond the stop round is left to the next stage — also one that was drawn
-            // before the flag was set and is still waiting here. (Without this a waiting item could outlive its
-            // predecessor's being dropped by a lane that saw the flag earlier: the two reads of the flag are not ordered
-            // with the queue's atomicAdd.) Items already running finish their segment: a ragged cut the next stage tolerates.
-            int sv = *(volatile int*)a.stop_seg;
-            if (LPR > 1) sv = __shfl_sync(gmask, sv, gleader);
-            if (wseg >= sv) { phase = PH_IDLE; ray = -1; exhausted = true; return; }
-        }
-        int d = atomicAdd(&a.seg_done[idx], 0);
-        if (LPR > 1) d = __shfl_sync(gmask, d, gleader);  // one observation for the whole group (another SM may write in between)
-        if (d == TORJ_SEG_RETIRED || d > wseg) {  // retired, or this segment was done by an earlier stage (ragged cut)
-            phase = PH_IDLE; ray = -1;
-        } else if (d == wseg && aligned) {
-            __threadfence();
-            if (wseg > 0) {
-                load_ray(idx);
-            } else if (a.B.status[idx] == 0) {
-                start_ray(idx);
-            } else {  // failed initialisation (k_ray_init): retire at once
-                if (writer) {
-                    atomicExch(&a.seg_done[idx], TORJ_SEG_RETIRED);
-                    atomicSub(a.rays_left, 1);
-                }
-                phase = PH_IDLE; ray = -1;
+        int verdict = 0;  // 0 void, 1 ready
+        if (writer) {
+            int w = atomicAdd(&a.seg_done[idx], 0);
+            for (;;) {
+                if (w == TORJ_SEG_RETIRED || TORJ_SEG_DONE(w) > wseg) break;  // retired / already run by its previous holder
+                if (TORJ_SEG_DONE(w) == wseg) { verdict = 1; break; }
+                const int drop = max(TORJ_SEG_DROP(w), wseg + 1);
+                const int old = atomicCAS(&a.seg_done[idx], w, TORJ_SEG_DONE(w) | (drop << 15));
+                if (old == w) break;  // dropped: the holder of the running segment will see the mark
+                w = old;
             }
+        }
+        if (LPR > 1) verdict = __shfl_sync(gmask, verdict, gleader);
+        if (verdict == 0) {
+            phase = PH_IDLE; ray = -1;
+        } else if (aligned) {
+            start_item(idx);
         } else {
-            phase = PH_WAIT;
+            own = false;
+            phase = PH_WAIT;  // ready, and mine: starts on the warp's next aligned trip
         }
     };
 
-    // item space of this launch: rounds first_seg .. n_segments-1 over the rays of ray_list (default: all rounds, all rays)
-    const long long n_round = a.ray_list ? (long long)__ldg(a.n_list) : n;
-    const int seg0 = a.first_seg ? min(__ldg(a.first_seg), O.n_segments) : 0;
-    const long long n_items = n_round * (long long)(O.n_segments - seg0);
+    // item space: item i = (round i / n, ray i % n); the ray's segment is the round, shifted by its predicted life
+    const int lmax = a.life ? __ldg(a.lmax) : 0;
+    const int n_rounds = O.n_segments + (a.life ? lmax - 1 : 0);  // a ray of predicted life 1 starts in round lmax - 1
+    const long long n_items = n * (long long)n_rounds;
     for (;;) {
         // ---- warp-ballot retire-and-refill: idle lanes draw the next work items from the global queue.
         // With segment hand-off a segment starts only on every (S-1)-th trip of the warp: a step is S-1 trips, so the
@@ -581,20 +593,21 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // <= 4 idle trips per segment, but measured +1.5 %: the fixed cadence is also what regroups stragglers.)
         const bool aligned = (cadence == 0);
         cadence = (cadence + 1 == S - 1) ? 0 : cadence + 1;
-        if (a.interleave && phase == PH_WAIT) claim(ray, aligned);
+        if (a.interleave && phase == PH_WAIT && aligned) {
+            if (own) phase = PH_RESUME;  // continuation: the state is here
+            else start_item(ray);
+        }
         unsigned need = __ballot_sync(FULL, phase == PH_IDLE && !exhausted);
         if (need) {
             int leader = __ffs(need) - 1;
             unsigned long long base = 0;
-            int left = 1, stop = 0x7fffffff;
+            int left = 1;
             if ((int)lane == leader) {
                 base = atomicAdd(a.next_ray, (unsigned long long)__popc(need & leaders));
                 if (a.interleave) left = atomicAdd(a.rays_left, 0);
-                if (a.stop_seg) stop = *(volatile int*)a.stop_seg;
             }
             base = __shfl_sync(FULL, base, leader);
             left = __shfl_sync(FULL, left, leader);
-            stop = __shfl_sync(FULL, stop, leader);
             if (phase == PH_IDLE && !exhausted) {
                 long long idx = (long long)base + __popc(need & leaders & ((1u << gleader) - 1u));
                 if (!a.interleave) {
@@ -608,16 +621,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     if (left == 0 || idx >= n_items) {
                         exhausted = true;
                     } else {
-                        const int round = (int)(idx / n_round);
-                        wseg = seg0 + round;
-                        long long r = idx - (long long)round * n_round;
-                        if (a.ray_list) r = __ldg(a.ray_list + r);
-                        // few rays left: finish this round, leave the following ones to the next stage. Items are handed
-                        // out in order, so nothing of a later round has been drawn yet (but for the lanes of this very
-                        // draw: a ragged cut, which claim() of the next stage tolerates)
-                        if (a.stop_seg && left <= a.stop_left && wseg + 1 < stop && writer) atomicMin(a.stop_seg, wseg + 1);
-                        if (wseg >= stop) exhausted = true;
-                        else claim(r, aligned);
+                        const int round = (int)(idx / n);
+                        const long long r = idx - (long long)round * n;
+                        wseg = a.life ? round - (lmax - __ldg(a.life + r)) : round;
+                        if (wseg >= 0 && wseg < O.n_segments) claim(r, aligned);  // else: the ray has not started yet / is over
                     }
                 }
             }
@@ -847,9 +854,20 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     phase = PH_IDLE;
                     act = ACT_NONE;
                 } else if (a.interleave) {
-                    save_ray();  // the next segment is a separate work item, usually taken by another lane
-                    ray = -1;
-                    phase = PH_IDLE;
+                    // hand the segment in. The next one is a separate work item, usually taken by another lane — unless that
+                    // item was drawn while this segment was still running and dropped (claim): then this lane keeps the ray
+                    save_ray();
+                    int old = 0;
+                    if (writer) old = atomicAdd(&a.seg_done[ray], 1);
+                    if (LPR > 1) old = __shfl_sync(gmask, old, gleader);
+                    if (TORJ_SEG_DROP(old) >= seg + 1) {
+                        wseg = seg;
+                        own = true;
+                        phase = PH_WAIT;  // next segment on the warp's next aligned trip
+                    } else {
+                        ray = -1;
+                        phase = PH_IDLE;
+                    }
                     act = ACT_NONE;
                 } else {
                     act = ACT_BEGIN_SEGMENT;
@@ -915,27 +933,38 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #endif
 }
 
-// Rays not yet retired, ascending (one block: the order keeps neighbouring rays on neighbouring lanes): input of a tail stage
-__global__ void k_compact_live(const int* __restrict__ seg_done, long long n, int* __restrict__ list, int* __restrict__ n_list) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (long long start = 0; start < n; start += blockDim.x) {
-        const long long i = start + threadIdx.x;
-        const bool live = i < n && seg_done[i] != TORJ_SEG_RETIRED;
-        const unsigned b = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) s_warp[w] = __popc(b);
-        __syncthreads();
-        int off = 0, total = 0;
-        for (int q = 0; q < nw; ++q) { const int c = s_warp[q]; if (q < w) off += c; total += c; }
-        if (live) list[s_base + off + __popc(b & ((1u << lane) - 1u))] = (int)i;
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
-        __syncthreads();
+// Predicted life of every ray in segments, for the order of the hand-off rounds only (never for a result): a straight march
+// from the plasma entry along the refracted direction, one point per segment end, with the real fields and the real
+// absorption coefficient there; P <- P exp(-alpha s_step) until the ray would stop (psi_N > psi_stop or P < p_stop,
+// reference src/solve.jl:174-176). Rays bend by millimetres over a segment: good to about one segment. ~100 RHS per ray
+// against ~21 000 in the trace.
+__global__ void k_predict_life(DevTables T, BundleDev B, SolverOpts O, int* __restrict__ life, int* __restrict__ lmax) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n_rays) return;
+    const long long n = B.n_rays;
+    int L = 1;
+    if (B.status[i] == 0) {
+        const double f = B.per_ray_fm ? B.freq[i] : B.freq[0];
+        const int mode = B.per_ray_fm ? B.mode[i] : B.mode[0];
+        const RayConst rc = make_ray_const(f, mode, O.te_min, O.max_harmonic, O.alpha_floor);
+        double u[7], du[9];
+        for (int q = 0; q < 7; ++q) u[q] = B.u0[(size_t)q * n + i];
+        const double in = rsqrt(u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
+        const double s_step = O.s_max / (double)O.n_segments;
+        const double dx = u[3] * in * s_step, dy = u[4] * in * s_step, dz = u[5] * in * s_step;
+        double P = 1.0;
+        Counters c = {0, 0, 0, 0, 0, 0, 0};
+        L = O.n_segments;
+        for (int k = 1; k <= O.n_segments; ++k) {
+            u[0] += dx; u[1] += dy; u[2] += dz;
+            rhs<true, true, true>(T, rc, u, du, c);
+            const double alpha = -du[6];  // u[6] = 1
+            if (alpha > 0.0) P *= exp(-alpha * s_step);
+            if (du[7] > O.psi_stop || P < O.p_stop || !(alpha == alpha)) { L = k; break; }
+        }
     }
-    if (threadIdx.x == 0) *n_list = s_base;
+    life[i] = L;
+    atomicMax(lmax, L);
 }
 
 // dP_dV[j] = bins[j] / (V(psi_{j+1}) - V(psi_j)); last entry 0 (reference src/plasma.jl:103,141)
