@@ -228,6 +228,15 @@ static int upload_warm_constants(torj_ctx* c) {
     fal[0] = 0.0;
     for (int m = 0; m < 8; ++m) { fct[m] = ref_fact(m); igam[m] = 1.0 / std::exp(ref_gammln(m + 1.5)); }
     CK(cudaMemcpyToSymbol(cw_comb, comb, sizeof comb));
+    double combs[7][4][6];
+    memset(combs, 0, sizeof combs);
+    for (int nq = -3; nq <= 3; ++nq)
+        for (int l = 1; l <= 3; ++l) {
+            const int is = nq < 0 ? -nq : nq;
+            if (is > l) continue;
+            for (int q = 0; q < 6; ++q) combs[nq + 3][l][q] = comb[is][l][q] * ((nq < 0 && (q == 1 || q == 3)) ? -1.0 : 1.0);
+        }
+    CK(cudaMemcpyToSymbol(cw_combs, combs, sizeof combs));
     CK(cudaMemcpyToSymbol(cw_fal, fal, sizeof fal));
     CK(cudaMemcpyToSymbol(cw_fact, fct, sizeof fct));
     CK(cudaMemcpyToSymbol(cw_igam, igam, sizeof igam));

@@ -82,6 +82,7 @@ __constant__ double cw_q2[9] = {3.97845977167414720840e+04, 3.972771091004145183
 // cw_fal[l] = -0.25^l (2l)!/(l!)^2 (the yg^(2(l-1)) divisor is applied at run time); cw_fact[m] = m!;
 // cw_igam[m] = 1/exp(gammln(m + 1.5)) with the reference's 6-term Lanczos gammln (:265-283), m = 0..7.
 __constant__ double cw_comb[6][6][6];
+__constant__ double cw_combs[7][4][6];  // the same for the quadrature, indexed [n + 3][l], with the sign of n folded into [1] and [3]
 __constant__ double cw_fal[6];
 __constant__ double cw_fact[8];
 __constant__ double cw_igam[8];
@@ -202,7 +203,6 @@ __device__ __noinline__ void warm_hermitian_warp(const double2* __restrict__ tab
 #pragma unroll 1
         for (int n = -llm; n <= llm; ++n) {
             const int nn = n < 0 ? -n : n;
-            const double sg = n < 0 ? -1.0 : 1.0;
             const double gr = fma(anpl, upl, (double)n * yg);
             const double zm = -amu * (gx - gr);
             const double s = amu * (gx + gr);
@@ -210,21 +210,22 @@ __device__ __noinline__ void warm_hermitian_warp(const double2* __restrict__ tab
             const double fe0m = expei_dev(zm);
             const double zf = zm * fe0m;
             if (nn == 0) H[18] = fma(-exdx * fe0m, upl2, H[18]);
-            // ffe for m = 1, 2, 3 (:691-697)
-            const double f1 = fma(s, 1.0 - zf, 1.0) * iamu2;
-            const double f2 = (6.0 - 2.0 * zm + 4.0 * s + s * s * (1.0 + zm - zm * zf)) * iamu4;
-            const double f3 = (18.0 * s * (s + 4.0 - zm) + 6.0 * (20.0 - 8.0 * zm + zm2) + s * s * s * (2.0 + zm + zm2 - zm2 * zf)) * iamu6;
+            // ffe for m = max(|n|, 1) .. llm (:691-697); n is warp-uniform, so these branches do not diverge
 #pragma unroll
             for (int l = 1; l <= 3; ++l) {
-                if (l >= nn && l >= 1 && l <= llm) {
-                    const double E = exdx * (l == 1 ? f1 : (l == 2 ? f2 : f3));
+                if (l >= nn && l <= llm) {
+                    double ffe;
+                    if (l == 1) ffe = fma(s, 1.0 - zf, 1.0) * iamu2;
+                    else if (l == 2) ffe = (6.0 - 2.0 * zm + 4.0 * s + s * s * (1.0 + zm - zm * zf)) * iamu4;
+                    else ffe = (18.0 * s * (s + 4.0 - zm) + 6.0 * (20.0 - 8.0 * zm + zm2) + s * s * s * (2.0 + zm + zm2 - zm2 * zf)) * iamu6;
+                    const double E = exdx * ffe;
                     const double E1 = E * upl, E2 = E * upl2;
-                    const double* cb = cw_comb[nn][l];
+                    const double* cb = cw_combs[n + 3][l];
                     double* h = H + 6 * (l - 1);
                     h[0] = fma(cb[0], E, h[0]);
-                    h[1] = fma(sg * cb[1], E, h[1]);
+                    h[1] = fma(cb[1], E, h[1]);
                     h[2] = fma(cb[2], E, h[2]);
-                    h[3] = fma(sg * cb[3], E1, h[3]);
+                    h[3] = fma(cb[3], E1, h[3]);
                     h[4] = fma(cb[4], E1, h[4]);
                     h[5] = fma(cb[5], E2, h[5]);
                 }
@@ -329,10 +330,10 @@ __device__ __noinline__ WarmOut warm_solve(const double* H, double xg, double yg
             for (int m = n; m <= lrm + 2; ++m) {
                 double c0 = cw_igam[m];
                 double sbi = c0;
-                for (int k = 1; k <= 50; ++k) {
-                    const double c1 = c0 * z2q / ((m + k) + 0.5) / k;
+                for (int k = 1; k <= 50; ++k) {  // c1 = c0 z2q / (m + k + 1/2) / k ; stop when c1 / sbi < 1e-10
+                    const double c1 = c0 * z2q * rcp_fast(((m + k) + 0.5) * (double)k);
                     sbi = sbi + c1;
-                    if (c1 / sbi < 1.0e-10) break;
+                    if (c1 < 1.0e-10 * sbi) break;
                     c0 = c1;
                 }
                 fs[m - n] = sbi;
