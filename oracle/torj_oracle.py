@@ -214,7 +214,7 @@ class OraclePlasma:
         posT, pp = _d(pos.T); dirT, pd = _d(dir.T); wt, pw = _d(weight)
         per_ray = int(np.ndim(freq) > 0)
         fr, pf = _d(np.atleast_1d(freq))
-        md = np.ascontiguousarray(np.atleast_1d(mode), dtype=np.int32)
+        md = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(mode), fr.shape), dtype=np.int32)  # per-ray f with one mode
         t, pt = _d(gl[0]); w, pgw = _d(gl[1]); g, pg = _d(psi_grid)
         prof = np.zeros(len(g)); dep = C.c_double()
         Pf = np.zeros(n); npts = np.zeros(n, dtype=np.int32); st = np.zeros(n, dtype=np.int32); cnt = np.zeros(5)

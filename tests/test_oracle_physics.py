@@ -128,3 +128,17 @@ def test_beam46_self_consistency(oracle_small, gl24, launcher):
     s = oracle_small.trace_bundle(pos, dirs, w, launcher["f"], 1, 0.5, psi, gl24, deposition="streaming")
     assert np.linalg.norm(s["dP_dV"] - r["dP_dV"]) / np.linalg.norm(r["dP_dV"]) < 1e-6
     assert s["counters"]["n_acc"] == r["counters"]["n_acc"] == int(np.sum(r["n_points"] - 2))
+
+
+def test_per_ray_frequency_with_one_mode(oracle_small, gl24, launcher):
+    """trace_bundle(freq per ray, mode scalar): the mode is broadcast (the C side indexes mode[i] whenever the frequency is per
+    ray; a length-1 array there read garbage modes for i > 0)."""
+    import torj_jl_b200 as tj
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
+                                             N_rings=2, min_azimuthal_points=3)
+    psi = np.linspace(0, 1, 50)
+    a = oracle_small.trace_bundle(pos, dirs, w, launcher["f"], 1, 0.5, psi, gl24, deposition="streaming")
+    b = oracle_small.trace_bundle(pos, dirs, w, np.full(len(w), launcher["f"]), 1, 0.5, psi, gl24, deposition="streaming")
+    assert np.array_equal(a["n_points"], b["n_points"]) and np.array_equal(a["P_final"], b["P_final"])
+    c = oracle_small.trace_bundle(pos, dirs, w, np.full(len(w), launcher["f"]), -1, 0.5, psi, gl24, deposition="streaming")
+    assert not np.array_equal(a["P_final"], c["P_final"])       # O-mode is a different ray

@@ -38,6 +38,9 @@ namespace torj {
 #ifndef TORJ_ROLL_DEPO
 #define TORJ_ROLL_DEPO 0  // 1: the three Newton steps of a level crossing as a real loop (smaller hot code)
 #endif
+#ifndef TORJ_ROLL_STENCIL
+#define TORJ_ROLL_STENCIL 0  // 1: the four Z rows of the 4x4 stencil as a real loop (row weights from polynomial tables)
+#endif
 #ifndef TORJ_PSI_LAZY
 #define TORJ_PSI_LAZY 0  // 1: psi_N rides on the stencil only at the stages whose psi is used. Measured SLOWER (134.6 -> 141.0 ms: the
                          // predicate costs more than the 37 DFMA it saves); kept for the record, off
@@ -153,6 +156,11 @@ __device__ __forceinline__ int bs_locate(double x, double x0, double inv_h, int 
     return i - 1;
 }
 
+// cubic B-spline weights as polynomials in the cell coordinate d, w_j = sum_k c_bsw[j][k] d^k, and their
+// derivatives: for the rolled row loop (TORJ_ROLL_STENCIL), where the row index is a run-time value
+__constant__ double c_bsw[4][4] = {{1.0 / 6.0, -0.5, 0.5, -1.0 / 6.0}, {2.0 / 3.0, 0.0, -1.0, 0.5}, {1.0 / 6.0, 0.5, 0.5, -0.5}, {0.0, 0.0, 0.0, 1.0 / 6.0}};
+__constant__ double c_bsd[4][3] = {{-0.5, 1.0, -0.5}, {0.0, -2.0, 1.5}, {0.5, 1.0, -1.5}, {0.0, 0.0, 0.5}};
+
 struct Fields {  // value, d/dR, d/dZ
     double BR, BR_R, BR_Z;
     double BZ, BZ_R, BZ_Z;
@@ -165,14 +173,32 @@ struct Fields {  // value, d/dR, d/dZ
 // all five RHS fields (and optionally psi_N) at a point inside the grid
 template <bool WITH_PSI>
 __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true) {
-    double wr[4], dwr[4], wz[4], dwz[4];
+    double wr[4], dwr[4];
     int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
+#if TORJ_ROLL_STENCIL
+    const double uz = (Z - T.z0) * T.inv_hz + 1.0;
+    int iz = (int)floor(uz);
+    iz = min(max(iz, 1), T.nZ - 1);
+    const double dz = uz - (double)iz;
+    const int bz = iz - 1;
+#else
+    double wz[4], dwz[4];
     int bz = bs_locate(Z, T.z0, T.inv_hz, T.nZ, wz, dwz);
+#endif
     double v[4] = {0, 0, 0, 0}, vR[4] = {0, 0, 0, 0}, vZ[4] = {0, 0, 0, 0};
     double te = 0.0, ps = 0.0, psR = 0.0, psZ = 0.0;
+#if TORJ_ROLL_STENCIL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int j = 0; j < 4; ++j) {
+#if TORJ_ROLL_STENCIL
+        const double wzj = fma(fma(fma(c_bsw[j][3], dz, c_bsw[j][2]), dz, c_bsw[j][1]), dz, c_bsw[j][0]);
+        const double dwzj = fma(fma(c_bsd[j][2], dz, c_bsd[j][1]), dz, c_bsd[j][0]) * T.inv_hz;
+#else
         const double wzj = wz[j], dwzj = dwz[j];
+#endif
         size_t node = (size_t)(bz + j) * T.row + br;
         const double2* pa = T.A + 2 * node;
         const double2* pb = T.B + node;

@@ -321,6 +321,9 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #define TORJ_ROLL_J 1  // 1: the stage-combination and error-estimate sums run as real loops over the stages: 170 hot instructions
                        // less against a 32 KB instruction cache (measured 132.0 -> 126.7 ms); 0 = fully unrolled
 #endif
+#ifndef TORJ_ST_BOUND
+#define TORJ_ST_BOUND 0  // 1 (with TORJ_ROLL_J): the stage combination sums the st stages that exist instead of all S-1 zero-padded ones
+#endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
 #endif
@@ -703,7 +706,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 #else
 #pragma unroll
 #endif
-                for (int j = 0; j < S - 1; ++j) {
+                for (int j = 0; j < ((TORJ_ST_BOUND && TORJ_ROLL_J) ? st : S - 1); ++j) {
                     const double aj = s_a[st][j];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) acc[i] = fma(aj, KK(j, i), acc[i]);
