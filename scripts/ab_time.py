@@ -43,6 +43,8 @@ def one():
         res["beam64k_dep"] = r["deposited_power"]
     ms, r = run(pl, pos, dirs, w, 95e9, reps=1, schedule=3, lanes_per_ray=1, alpha_floor=0.0)
     res["beam64k_exact"] = ms
+    ms, r = run(pl, pos, dirs, w, 95e9, reps=2, lanes_per_ray=1, beam_id=np.zeros(len(w), dtype=np.int32), n_beams=2)
+    res["beam64k_global_atomics"] = ms  # n_beams > 1 books straight into global memory: all 65 543 rays into ONE row
     pa, da, wa = bench.sweep_bundle()
     idx = shard_block_cyclic(len(wa), 1025, 0, 8)
     for sch in (3, 0):

@@ -374,7 +374,10 @@ def test_multi_gpu_front_end_collective_and_sharding(gpu_small, launcher):
         for sharding, det in (("contiguous", False), ("block_cyclic", False), ("block_cyclic", True)):
             mg.configure(sharding=sharding, block_rays=per, deterministic=det)
             r = mg.trace_bundle(gpu_small, pos, dirs, w, 95e9, 1, 0.6, psi, beam_id=bid, n_beams=len(Ls))
-            assert mg.used_nccl == (ndev > 1 and not det), (sharding, det, ndev)
+            # the collective needs every device of the communicator: with fewer beams (blocks) than devices the idle devices
+            # stay out and the profiles are summed on the host
+            all_busy = sharding == "contiguous" or len(Ls) >= ndev
+            assert mg.used_nccl == (ndev > 1 and not det and all_busy), (sharding, det, ndev)
             assert np.array_equal(r["n_points"], one["n_points"]) and np.array_equal(r["status"], one["status"])
             assert np.abs(r["P_final"] - one["P_final"]).max() < 1e-11
             assert np.abs(r["dP_dV"] - one["dP_dV"]).max() <= 1e-9 * np.abs(one["dP_dV"]).max()
