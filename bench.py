@@ -457,7 +457,7 @@ def run_gpu_arm(args, wl):
     if n_exact:
         device_step(opt_exact)
         exact_ms = timed(n_exact, opt_exact) / n_exact
-    device_step()  # counters above stay those of the default options; leave the bundle in its default state
+        device_step()  # leave the bundle as the default options traced it
 
     # ---- end to end through the reference-facing call with HOST buffers (H2D of the bundle, D2H of the results)
     e2e = None
