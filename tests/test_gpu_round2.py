@@ -157,6 +157,33 @@ def test_warm_beam_gate_and_mappings_agree(gl24, launcher):
     assert ref["deposited_power"] > 0.01
 
 
+def test_config5_warm_multi_launcher_multi_frequency_scan(gl24):
+    """BASELINE.json configs[4] in small: 2 launchers (z = +-0.4 m) x {110, 170} GHz on the T_e0 = 15 keV equilibrium, warm model,
+    per-ray frequency, one profile per beam, one device call; every beam's absorbed fraction (rel 1e-6) and profile (L2 1e-4)
+    against the oracle traced beam by beam, and the up-down symmetry of the Solov'ev equilibrium."""
+    arr = hot_arrays(129, 15e3)
+    pl, opl = tj.Plasma(*arr.values()), O.OraclePlasma(*arr.values())
+    psi = np.linspace(0.0, 1.0, 200)
+    P, D, W, F, B, beams = [], [], [], [], [], []
+    for z in (0.4, -0.4):
+        for f in (110e9, 170e9):
+            N0 = tj.pol_tor_angles_2_vector(np.deg2rad(30.0 if z > 0 else -30.0), 0.0)
+            p, d, w = tj.launch_peripheral_rays(np.array([2.5, 0.0, z]), N0, 0.0174, 1 / 3.99, f, N_rings=2, min_azimuthal_points=3)
+            beams.append((p, d, w, f))
+            P.append(p); D.append(d); W.append(w); F.append(np.full(len(w), f)); B.append(np.full(len(w), len(beams) - 1, dtype=np.int32))
+    P, D, W, F, B = map(np.concatenate, (P, D, W, F, B))
+    res = tj.trace_bundle(pl, P, D, W, F, 1, 0.7, psi, options=tj.default_options(absorption_model=1), beam_id=B, n_beams=4)
+    assert (res["status"] == 0).all() and res["dP_dV"].shape == (4, 200)
+    for b, (p, d, w, f) in enumerate(beams):
+        ref = opl.trace_bundle(p, d, w, f, 1, 0.7, psi, gl24, opts=O.OracleOptions.default(absorption_model=1))
+        assert (ref["status"] == 0).all() and np.array_equal(res["n_points"][B == b], ref["n_points"])
+        assert abs(res["deposited_power"][b] - ref["deposited_power"]) <= FRAC_TOL * ref["deposited_power"], (b, f)
+        assert l2rel(res["dP_dV"][b], ref["dP_dV"]) < L2_FAITHFUL
+        assert np.abs(res["P_final"][B == b] - ref["P_final"]).max() < 1e-8
+    assert res["deposited_power"][1] < res["deposited_power"][0] and res["deposited_power"][0] > 0.99   # 3rd harmonic (170 GHz) absorbs less
+    assert np.abs(res["deposited_power"][:2] - res["deposited_power"][2:]).max() < 1e-9   # mirror launchers
+
+
 def test_warm_model_option_validation(gpu_small, launcher):
     for kw in (dict(absorption_model=2), dict(lanes_per_ray=16), dict(absorption_model=1, lanes_per_ray=8), dict(absorption_model=1, max_harmonic=5)):
         with pytest.raises(tj.TorjError):

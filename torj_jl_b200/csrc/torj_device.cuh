@@ -421,9 +421,46 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
 // scaled by 2^k built in the exponent field.
 __constant__ double c_exp[17];  // log2(e), -ln2_hi, -ln2_lo, 1/13!, 1/12!, ..., 1/2!, 1, 1 (constant-bank operands: a
                                 // 64-bit literal costs two extra issue slots per use, a c[][] operand none)
+#ifndef TORJ_EXP_TABLE
+#define TORJ_EXP_TABLE 0  // 1: exp from a 64-entry table of 2^(j/64) (L1-resident) and a degree-5 polynomial instead of degree 13
+#endif
+__device__ const double d_exp_tab[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951,
+};
 __device__ __forceinline__ double exp_fast(double x) {
     x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
     x = x > 708.0 ? 708.0 : x;
+#if TORJ_EXP_TABLE
+    {
+        // n = rint(64 x / ln2) = 64 k + j ; r = x - n ln2/64 (|r| <= ln2/128: r^6/720 < 4e-17) ; exp(x) = 2^k 2^(j/64) p(r)
+        const double nd = rint(x * 92.33248261689366);
+        double r = fma(nd, -0.01083042469326756, x);
+        r = fma(nd, -2.9815858269852933e-12, r);
+        const int n = (int)nd;
+        const double t = __ldg(d_exp_tab + (n & 63));
+        double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+        p = fma(p, r, 1.0 / 6.0);
+        p = fma(p, r, 0.5);
+        p = fma(p, r, 1.0);
+        p = fma(p, r, 1.0);
+        return (t * p) * __hiloint2double(((n >> 6) + 1023) << 20, 0);
+    }
+#endif
     const double kd = rint(x * c_exp[0]);
     double r = fma(kd, c_exp[1], x);
     r = fma(kd, c_exp[2], r);
