@@ -956,7 +956,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         if (model == 1) lpr = (b->n <= lanes_guess / 2) ? 32 : 1;
         else lpr = (b->n * 8 <= lanes_guess) ? 8 : 1;
     }
-    size_t smem = (size_t)n_psi * sizeof(double);
+    size_t smem = (size_t)TORJ_BIN_WORDS(n_psi) * sizeof(double);
     if (model == 1 && lpr == 1) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
 #if TORJ_K_SMEM
     smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
@@ -1002,7 +1002,9 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (interleave && model == 0 && od.schedule != 3) {
         if (!b->d_life) CK(cudaMalloc(&b->d_life, ((size_t)b->n + 1) * sizeof(int)));
         CK(cudaMemsetAsync(b->d_life + b->n, 0, sizeof(int), st));
-        k_predict_life<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so, b->d_life, b->d_life + b->n);
+        const char* hc = getenv("TORJ_LIFE_HARM_COST");  // (experiment) weight of one evaluated harmonic in the predicted cost
+        k_predict_life<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so, hc ? atof(hc) : TORJ_LIFE_HARM_COST, b->d_life,
+                                                                       b->d_life + b->n);
         c->launches++;
         CK(cudaGetLastError());
         a.life = b->d_life; a.lmax = b->d_life + b->n;

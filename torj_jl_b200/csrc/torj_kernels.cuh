@@ -1,7 +1,7 @@
 // Kernels of libtorj_cuda.so (sm_100a).
 //   k_ray_init : first_point + vacuum_plasma_refraction, one thread per ray   (reference src/solve.jl:18-74,137-144)
 //   k_trace    : persistent one-thread-per-ray integrator with warp-ballot retire-and-refill of finished rays,
-//                streaming psi-shell deposition into shared-memory bins       (reference src/solve.jl:154-177, src/plasma.jl:91-151)
+//                streaming psi-shell deposition into the profile row           (reference src/solve.jl:154-177, src/plasma.jl:91-151)
 //   k_finalize : bins / dV -> dP_dV                                            (reference src/plasma.jl:141, src/solve.jl:233-240)
 //   k_probe, k_rhs : point probes for parity tests; k_dfma : FP64 peak microbenchmark
 #pragma once
@@ -260,7 +260,7 @@ struct TraceArgs {
     SolverOpts O;
     TrajDev J;
     int n_psi;
-    int n_beams;                      // > 1: one profile per beam, booked straight into global memory
+    int n_beams;                      // one profile row per beam, booked with global-memory RED.ADD.F64
     const int* beam_id;               // [n] (n_beams > 1 only)
     const double* psi_edges;          // [n_psi]
     double* bins;                     // [n_beams][n_psi+2]: weighted shell power, then sum w_i P_i and sum w_i
@@ -278,7 +278,7 @@ struct TraceArgs {
     double* u_final;                  // [7][n] state of every ray at retirement, or NULL
     // life-ordered rounds (k_predict_life): ray r's segment k is item (round k + lmax - life[r], r), so that long-lived rays
     // start first and all rays END together — no tail of a few long rays running alone. NULL = every ray starts in round 0
-    const int* life;                  // [n] predicted number of segments of every ray, 1 .. n_segments
+    const int* life;                  // [n] predicted cost of every ray in rounds (segments, those inside the absorbing layer weighted)
     const int* lmax;                  // max of life[]
 };
 #define TORJ_HAND_D 20
@@ -310,6 +310,11 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_TPB
 #define TORJ_TPB 128
 #endif
+#ifndef TORJ_SMEM_BINS
+#define TORJ_SMEM_BINS 0  // 1: single-profile bundles book into block-local shared-memory bins flushed at the end (round 1).
+#endif                    //    Measured SLOWER than booking straight into global memory (119.6 against 117.8 ms on the 65 543-ray
+                          //    beam): a shared-memory FP64 atomicAdd is a CAS loop, a global one is a fire-and-forget RED.ADD.F64.
+#define TORJ_BIN_WORDS(n_psi) (TORJ_SMEM_BINS ? (n_psi) : 0)
 #ifndef TORJ_K_SMEM
 #define TORJ_K_SMEM 1  // 1: Runge-Kutta stage derivatives k[S][7] live in shared memory instead of (L1-backed) local memory
 #endif
@@ -324,6 +329,9 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #ifndef TORJ_ST_BOUND
 #define TORJ_ST_BOUND 1  // 1 (with TORJ_ROLL_J): the stage combination sums the st stages that exist instead of all S-1 zero-padded
                          // ones (the cadence keeps the lanes of a warp at the same stage): 121.9 -> 119.8 ms
+#endif
+#ifndef TORJ_LIFE_HARM_COST
+#define TORJ_LIFE_HARM_COST 0.0  // k_predict_life: extra rounds one evaluated harmonic integral per pilot point adds to a ray's cost
 #endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
@@ -361,10 +369,12 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
     extern __shared__ double smem[];
+#if TORJ_SMEM_BINS
     double* s_bins = smem;                                 // [n_psi] block-local deposition bins
+#endif
     const double* __restrict__ s_edges = a.psi_edges;      // psi levels: read-only, through L1 (__ldg)
 #if TORJ_K_SMEM
-    double* ks = smem + a.n_psi + threadIdx.x;             // KK(j, i) at ks[(j*7+i)*TORJ_TPB]: conflict-free
+    double* ks = smem + TORJ_BIN_WORDS(a.n_psi) + threadIdx.x;             // KK(j, i) at ks[(j*7+i)*TORJ_TPB]: conflict-free
 #define KK(j, i) ks[((j) * 7 + (i)) * TORJ_TPB]
 #else
     double k_loc[S][7];
@@ -374,7 +384,9 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     __shared__ double s_tot[2];
     __shared__ double s_a[7][7], s_bt[7];
     const int n_psi = a.n_psi;
+#if TORJ_SMEM_BINS
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x) s_bins[j] = 0.0;
+#endif
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0.0;
     if (threadIdx.x < 49) s_a[threadIdx.x / 7][threadIdx.x % 7] = c_tab[SCH].a[threadIdx.x / 7][threadIdx.x % 7];
@@ -406,7 +418,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     // sits at the 255-register limit and the compiler, not knowing trip frequencies, otherwise spills values that
     // every RHS evaluation touches (ray constants, counters) to local memory (122 -> 72 bytes of spills, -1 % time;
     // parking the once-per-step scalars as well removes the spills altogether but gains nothing more).
-    double* pk = smem + a.n_psi + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + threadIdx.x;
+    double* pk = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + threadIdx.x;
 #define PK(k) pk[(k) * TORJ_TPB]
     long long& ray = *reinterpret_cast<long long*>(&PK(0));
     long long& tj = *reinterpret_cast<long long*>(&PK(1));  // index into the trajectory window or -1
@@ -430,7 +442,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     unsigned int rays_ok = 0;
 #endif
     // warm model, one ray per lane: shared-memory slots where a lane's quadrature sums wait for the serial solve
-    double* wstash = smem + a.n_psi + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + (TORJ_PARK ? TORJ_PARK_SLOTS * TORJ_TPB : 0) + threadIdx.x;
+    double* wstash = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + (TORJ_PARK ? TORJ_PARK_SLOTS * TORJ_TPB : 0) + threadIdx.x;
     int phase = PH_IDLE, st = 0;
     bool exhausted = false;
     double u[7], tmp[7];
@@ -456,8 +468,11 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     auto sink = [&](int shell, double dP) {
         pdep += dP;
         if (!writer) return;
-        if (a.n_beams > 1) atomicAdd(&beam_bins[shell], wgt * dP);
-        else atomicAdd(&s_bins[shell], wgt * dP);
+#if TORJ_SMEM_BINS
+        if (a.n_beams == 1) atomicAdd(&s_bins[shell], wgt * dP);
+        else
+#endif
+            atomicAdd(&beam_bins[shell], wgt * dP);
         if (tj >= 0) atomicAdd(&a.J.prof[tj * n_psi + shell], dP);  // (a ray may change SMs between segments)
     };
     auto put_point = [&](double s, const double* xx, double P, double dP) {
@@ -926,8 +941,10 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         for (int q = 0; q < 8; ++q) atomicAdd(&s_cnt[q], c6[q]);
     }
     __syncthreads();
+#if TORJ_SMEM_BINS
     for (int j = threadIdx.x; j < n_psi; j += blockDim.x)
         if (s_bins[j] != 0.0) atomicAdd(&a.bins[j], s_bins[j]);
+#endif
     if (threadIdx.x < 2) atomicAdd(&a.bins[n_psi + threadIdx.x], s_tot[threadIdx.x]);
     if (threadIdx.x < 8) atomicAdd(&a.counters[threadIdx.x], s_cnt[threadIdx.x]);
 #undef KK
@@ -946,10 +963,11 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 // kernel draws 32 consecutive items, and they must be all real or all void — lanes that each skip ahead to their own next
 // real item would end up with rays from all over the bundle, and neighbouring rays on neighbouring lanes is what keeps
 // the stencil loads and the absorbing layer coherent (a random ray order costs 40 %).
-__global__ void k_predict_life(DevTables T, BundleDev B, SolverOpts O, int* __restrict__ life, int* __restrict__ lmax) {
+__global__ void k_predict_life(DevTables T, BundleDev B, SolverOpts O, double harm_cost, int* __restrict__ life,
+                               int* __restrict__ lmax) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: warp = ray block
     const long long n = B.n_rays;
-    int L = 1;
+    double cost = 1.0;
     if (i < n && B.status[i] == 0) {
         const double f = B.per_ray_fm ? B.freq[i] : B.freq[0];
         const int mode = B.per_ray_fm ? B.mode[i] : B.mode[0];
@@ -961,15 +979,18 @@ __global__ void k_predict_life(DevTables T, BundleDev B, SolverOpts O, int* __re
         const double dx = u[3] * in * s_step, dy = u[4] * in * s_step, dz = u[5] * in * s_step;
         double P = 1.0;
         Counters c = {0, 0, 0, 0, 0, 0, 0};
-        L = O.n_segments;
+        cost = 0.0;
         for (int k = 1; k <= O.n_segments; ++k) {
             u[0] += dx; u[1] += dy; u[2] += dz;
+            const unsigned long long h0 = c.n_harm;
             rhs<true, true, true>(T, rc, u, du, c);
+            cost += 1.0 + harm_cost * (double)(c.n_harm - h0);  // a segment inside the absorbing layer costs more trips' worth
             const double alpha = -du[6];  // u[6] = 1
             if (alpha > 0.0) P *= exp(-alpha * s_step);
-            if (du[7] > O.psi_stop || P < O.p_stop || !(alpha == alpha)) { L = k; break; }
+            if (du[7] > O.psi_stop || P < O.p_stop || !(alpha == alpha)) break;
         }
     }
+    int L = (int)ceil(cost);
     L = __reduce_max_sync(0xffffffffu, L);
     if (i < n) life[i] = L;
     if ((threadIdx.x & 31) == 0) atomicMax(lmax, L);
