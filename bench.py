@@ -616,6 +616,8 @@ def run_multi_arm(args, wl):
     mg.abs_Al_init(N_GL)
     pl = tj.Plasma(*tj.solovev_arrays(GRID, GRID).values(), build="device")
     pos, dirs, w = sweep_bundle() if wl == "sweep1m" else beam_bundle(wl)
+    # column-major (n, 3), the layout of a Julia Matrix[n, 3]: the library's component-major [3][n] without a copy
+    pos, dirs = np.asfortranarray(pos), np.asfortranarray(dirs)
     mg.configure(sharding="block_cyclic" if wl == "sweep1m" else "contiguous", block_rays=1025, deterministic=args.deterministic)
     psi = np.linspace(0.0, 1.0, N_PSI)
     opt = _lib.default_options(schedule=args.schedule)
@@ -631,7 +633,7 @@ def run_multi_arm(args, wl):
     line = {"metric": "ray-steps/s", "value": v, "unit": "ray-steps/s", "n_gpus": mg.n_devices, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "multi", "config": make_config(wl, args),
-            "timing": "host wall clock around the blocking torj_multi_trace call (host buffers in, results out): an end-to-end number",
+            "timing": "host wall clock around the blocking torj_multi_trace call (host buffers in Julia's column-major layout, results out): an end-to-end number",
             "collective": "ncclAllReduce on the devices' profile buffers" if mg.used_nccl else "host sum in device order",
             "rays_per_s": n / (ms * 1e-3), "absorbed_fraction": r["deposited_power"],
             "e2e": {"value": v, "unit": "ray-steps/s", "h2d_bytes_per_step": 8 * 7 * n, "d2h_bytes_per_step": 8 * (N_PSI + 2 + 2 * n) + 8 * n,

@@ -1002,9 +1002,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     if (interleave && model == 0 && od.schedule != 3) {
         if (!b->d_life) CK(cudaMalloc(&b->d_life, ((size_t)b->n + 1) * sizeof(int)));
         CK(cudaMemsetAsync(b->d_life + b->n, 0, sizeof(int), st));
-        const char* hc = getenv("TORJ_LIFE_HARM_COST");  // (experiment) weight of one evaluated harmonic in the predicted cost
-        k_predict_life<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so, hc ? atof(hc) : TORJ_LIFE_HARM_COST, b->d_life,
-                                                                       b->d_life + b->n);
+        k_predict_life<<<(unsigned)((b->n + 127) / 128), 128, 0, st>>>(p->T, b->B, so, TORJ_LIFE_HARM_COST, b->d_life, b->d_life + b->n);
         c->launches++;
         CK(cudaGetLastError());
         a.life = b->d_life; a.lmax = b->d_life + b->n;

@@ -331,7 +331,9 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
                          // ones (the cadence keeps the lanes of a warp at the same stage): 121.9 -> 119.8 ms
 #endif
 #ifndef TORJ_LIFE_HARM_COST
-#define TORJ_LIFE_HARM_COST 0.0  // k_predict_life: extra rounds one evaluated harmonic integral per pilot point adds to a ray's cost
+#define TORJ_LIFE_HARM_COST 0.25  // k_predict_life: rounds one evaluated harmonic integral per pilot point adds to a ray's predicted
+                                  // cost (segments inside the absorbing layer take longer). 1/16 and 1/8 shards of the 1 M-ray sweep:
+                                  // 0 -> 174.8 / 299.2 ms, 0.25 -> 166.7 / 288.9, 0.5 -> 168.1 / 291.0, 0.75 -> 176.3 / 295.3; beam unchanged
 #endif
 #ifndef TORJ_MINB
 #define TORJ_MINB 2  // resident CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128)
