@@ -81,10 +81,10 @@ typedef struct torj_options {
                                       (te_min); the debug assertion at :314-316 is dropped (it calls an un-imported function).
                                       With alpha_floor > 0 the 501-node quadrature is skipped where the anti-Hermitian part is
                                       below the floor by construction (torj_warm.cuh); 0 evaluates it everywhere */
-    int32_t lanes_per_ray;         /* 0 = automatic; 1 = one GPU thread per ray; 8 / 32 = a group of 8 lanes / a warp per ray (the
-                                      nodes of the harmonic integrals / of the warm quadrature are split over the lanes): for
-                                      bundles below the resident lanes, where the time is one ray's latency, and for the warm
-                                      model (1 or 32 only). Results agree to rounding (summation order) */
+    int32_t lanes_per_ray;         /* 0 = automatic; 1 = one GPU thread per ray; 2 / 4 / 8 / 32 = a group of lanes / a warp per ray
+                                      (the nodes of the harmonic integrals / of the warm quadrature are split over the lanes):
+                                      for bundles below the resident lanes, where the time is one ray's latency, and for the
+                                      warm model (1 or 32 only). Results agree to rounding (summation order) */
     int32_t reserved_;             /* keeps the struct size a multiple of 8; must be 0 */
 } torj_options;
 

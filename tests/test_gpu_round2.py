@@ -268,12 +268,12 @@ def test_life_ordered_rounds_give_the_same_rays(gpu_full, oracle_full, gl24, lau
     assert len(np.unique(a["n_points"])) > 3
 
 
-def test_eight_lanes_per_ray(gpu_small, oracle_small, gl24, launcher):
+def test_several_lanes_per_ray(gpu_small, oracle_small, gl24, launcher):
     pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], launcher["N0"], launcher["spot"], launcher["inv_Rc"], launcher["f"],
                                              N_rings=4, min_azimuthal_points=7)
     psi = np.linspace(0, 1, 120)
     runs = [tj.trace_bundle(gpu_small, pos, dirs, w, launcher["f"], 1, 0.8, psi, options=tj.default_options(lanes_per_ray=l, schedule=s))
-            for l, s in ((1, 1), (8, 1), (8, 2), (32, 2))]
+            for l, s in ((1, 1), (8, 1), (8, 2), (32, 2), (2, 0), (4, 0), (4, 1))]
     for r in runs[1:]:
         assert np.array_equal(r["n_points"], runs[0]["n_points"]) and r["counters"] == runs[0]["counters"]
         assert np.abs(r["P_final"] - runs[0]["P_final"]).max() < 1e-12 and l2rel(r["dP_dV"], runs[0]["dP_dV"]) < 1e-11

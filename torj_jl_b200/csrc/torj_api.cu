@@ -589,6 +589,8 @@ static trace_kernel_t pick_trace_kernel(int scheme, bool high, int model, int lp
                                      : (z3 ? k_trace<1, false, 1, 1> : k_trace<0, false, 1, 1>);
     if (lpr == 32) return high ? (z3 ? k_trace<1, true, 0, 32> : k_trace<0, true, 0, 32>) : (z3 ? k_trace<1, false, 0, 32> : k_trace<0, false, 0, 32>);
     if (lpr == 8) return high ? (z3 ? k_trace<1, true, 0, 8> : k_trace<0, true, 0, 8>) : (z3 ? k_trace<1, false, 0, 8> : k_trace<0, false, 0, 8>);
+    if (lpr == 4) return high ? (z3 ? k_trace<1, true, 0, 4> : k_trace<0, true, 0, 4>) : (z3 ? k_trace<1, false, 0, 4> : k_trace<0, false, 0, 4>);
+    if (lpr == 2) return high ? (z3 ? k_trace<1, true, 0, 2> : k_trace<0, true, 0, 2>) : (z3 ? k_trace<1, false, 0, 2> : k_trace<0, false, 0, 2>);
     return high ? (z3 ? k_trace<1, true> : k_trace<0, true>) : (z3 ? k_trace<1, false> : k_trace<0, false>);
 }
 
@@ -890,9 +892,11 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
         FAIL("torj_bundle_trace: schedule must be 0 (automatic), 1 (whole rays), 2 (segment hand-off) or 3 (hand-off without tail stages)");
     if (od.max_steps_per_segment < 1) FAIL("torj_bundle_trace: max_steps_per_segment < 1");
     if (od.absorption_model != 0 && od.absorption_model != 1) FAIL("torj_bundle_trace: absorption_model must be 0 (Albajar) or 1 (warm)");
-    if (od.lanes_per_ray != 0 && od.lanes_per_ray != 1 && od.lanes_per_ray != 8 && od.lanes_per_ray != 32)
-        FAIL("torj_bundle_trace: lanes_per_ray must be 0 (automatic), 1, 8 or 32");
-    if (od.absorption_model == 1 && od.lanes_per_ray == 8) FAIL("torj_bundle_trace: the warm model runs with 1 or 32 lanes per ray");
+    if (od.lanes_per_ray != 0 && od.lanes_per_ray != 1 && od.lanes_per_ray != 2 && od.lanes_per_ray != 4 && od.lanes_per_ray != 8 &&
+        od.lanes_per_ray != 32)
+        FAIL("torj_bundle_trace: lanes_per_ray must be 0 (automatic), 1, 2, 4, 8 or 32");
+    if (od.absorption_model == 1 && od.lanes_per_ray > 1 && od.lanes_per_ray < 32)
+        FAIL("torj_bundle_trace: the warm model runs with 1 or 32 lanes per ray");
     if (od.absorption_model == 1 && od.max_harmonic > 3) FAIL("torj_bundle_trace: max_harmonic > 3 belongs to the Albajar model; the warm model takes its harmonics from larmornumber");
     if (!(s_max > 0.0)) FAIL("torj_bundle_trace: s_max must be > 0");
     if (set_device(c)) return 1;
@@ -945,16 +949,17 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     a.warm_tab = c->d_warm_tab; a.u_final = b->d_ufinal;
     const int model = od.absorption_model;
     // Several lanes per ray when the bundle cannot fill the GPU with one thread per ray — then the time is one ray's
-    // latency, and splitting the quadrature nodes over the lanes of a group shortens exactly that. Measured on 1 025 /
-    // 4 100-ray bundles (profiles/): cold 4 keV beam 54 (1 lane) / 52 (8) / 61 ms (32); 10 keV scan 282 / 220-239 / 170 ms
-    // per wave — but 32 lanes per ray fit only 1 184 rays at a time (4 100 rays: 600 ms). 8 lanes per ray up to an eighth
-    // of the resident lanes (4 736 rays) is never worse than one lane and close to the best everywhere. The warm model,
-    // whose alpha is ~100x the rest of the RHS and warp-cooperative either way, takes a warp per ray up to half the lanes.
+    // latency, and splitting the quadrature nodes over the lanes of a group shortens exactly that. Measured
+    // (profiles/r02_lanes_per_ray.json), ms for 1 / 2 / 4 / 8 lanes: cold 4 keV beam of 1 025 rays 54.9 / 53.2 / 51.9 / 52.1;
+    // 10 keV scans of 1 025 rays 215 / 183 / 151 / 150, 4 100 rays 293 / 241 / 211 / 231, 8 200 rays 290 / 248 / 242 / 303,
+    // 16 400 rays 316 / 304 / 332 / 620 (32 lanes fit only 1 184 rays at a time: 4 100 rays 576). Hence: the widest group
+    // that still fits all rays at once, 8 lanes only while that leaves every scheduler a single warp. The warm model, whose
+    // alpha is ~100x the rest of the RHS and warp-cooperative either way, takes a warp per ray up to half the lanes.
     const int64_t lanes_guess = (int64_t)c->num_sms * TORJ_MINB * TORJ_TPB;
     int lpr = od.lanes_per_ray;
     if (lpr == 0) {
         if (model == 1) lpr = (b->n <= lanes_guess / 2) ? 32 : 1;
-        else lpr = (b->n * 8 <= lanes_guess) ? 8 : 1;
+        else lpr = (b->n * 8 <= lanes_guess / 2) ? 8 : (b->n * 4 <= lanes_guess) ? 4 : (b->n * 2 <= lanes_guess) ? 2 : 1;
     }
     size_t smem = (size_t)TORJ_BIN_WORDS(n_psi) * sizeof(double);
     if (model == 1 && lpr == 1) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);

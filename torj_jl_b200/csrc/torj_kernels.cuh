@@ -403,8 +403,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     const bool writer = (lane & (unsigned)(LPR - 1)) == 0;  // the lane that performs a ray's side effects
     const unsigned gmask = group_mask(LPR);                 // the lanes that hold my ray
     const unsigned gleader = lane & ~(unsigned)(LPR - 1);
-    const unsigned leaders = LPR == 1 ? FULL : (LPR == 32 ? 1u : 0x01010101u);
-    static_assert(LPR == 1 || LPR == 8 || LPR == 32, "lanes per ray");
+    const unsigned leaders = LPR == 1 ? FULL : LPR == 2 ? 0x55555555u : LPR == 4 ? 0x11111111u : LPR == 8 ? 0x01010101u : 1u;
+    static_assert(LPR == 1 || LPR == 2 || LPR == 4 || LPR == 8 || LPR == 32, "lanes per ray");
     const double beta1 = 7.0 / (10.0 * ORDER), beta2 = 2.0 / (5.0 * ORDER);
     const double gamma_c = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1e-4;
     // OrdinaryDiffEq's step_accept_controller! holds the step (q := 1) when qsteady_min = 1 <= q <= qsteady_max = 1.2.
