@@ -66,8 +66,7 @@ struct torj_plasma {
     torj_ctx* ctx = nullptr;
     uint64_t id = 0;  // unique per created plasma (addresses can be recycled)
     DevTables T{};
-    double2* dA = nullptr;
-    double2* dB = nullptr;
+    double2* dA = nullptr;  // [nodes][3]
     DevTables* dT = nullptr;  // T mirrored in global memory
     // host copy of the V(psi_N) spline (reference src/plasma.jl:42-44)
     std::vector<double> vol_c;
@@ -404,25 +403,24 @@ int torj_plasma_create(torj_ctx* c, const torj_grid* g, const double* coef_psi, 
                        torj_plasma** out) {
     if (!c || !g || !out) FAIL("torj_plasma_create: NULL argument");
     if (g->nR < 2 || g->nZ < 2 || n_vol < 2) FAIL("torj_plasma_create: grid too small");
+    if ((double)(g->nR + 2) * (double)(g->nZ + 2) >= 2147483648.0) FAIL("torj_plasma_create: grid too large (2^31 nodes)");
     if (set_device(c)) return 1;
     torj_plasma* p = new torj_plasma();
     Guard<torj_plasma, torj_plasma_destroy> guard(p);
     p->ctx = c;
     p->id = ++g_plasma_serial;
     size_t nodes = (size_t)(g->nR + 2) * (g->nZ + 2);
-    std::vector<double2> hA(2 * nodes), hB(nodes);
+    std::vector<double2> hA(3 * nodes);
     for (size_t k = 0; k < nodes; ++k) {
-        hA[2 * k] = make_double2(coef_BR[k], coef_BZ[k]);
-        hA[2 * k + 1] = make_double2(coef_Bphi[k], coef_lnne[k]);
-        hB[k] = make_double2(coef_lnTe[k], coef_psi[k]);
+        hA[3 * k] = make_double2(coef_BR[k], coef_BZ[k]);
+        hA[3 * k + 1] = make_double2(coef_Bphi[k], coef_lnne[k]);
+        hA[3 * k + 2] = make_double2(coef_lnTe[k], coef_psi[k]);
     }
-    CK(cudaMalloc(&p->dA, 2 * nodes * sizeof(double2)));
-    CK(cudaMalloc(&p->dB, nodes * sizeof(double2)));
-    CK(cudaMemcpyAsync(p->dA, hA.data(), 2 * nodes * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(p->dB, hB.data(), nodes * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMalloc(&p->dA, 3 * nodes * sizeof(double2)));
+    CK(cudaMemcpyAsync(p->dA, hA.data(), 3 * nodes * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     DevTables& T = p->T;
-    T.A = p->dA; T.B = p->dB;
+    T.A = p->dA;
     T.nR = g->nR; T.nZ = g->nZ; T.row = g->nR + 2;
     T.r0 = g->R_first; T.z0 = g->Z_first;
     double hr = (g->R_last - g->R_first) / (double)(g->nR - 1), hz = (g->Z_last - g->Z_first) / (double)(g->nZ - 1);
@@ -477,6 +475,7 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
                                  int32_t n_1d, torj_plasma** out) {
     if (!c || !g || !out) FAIL("torj_plasma_create_from_data: NULL argument");
     if (g->nR < 2 || g->nZ < 2 || n_prof < 4 || n_1d < 2) FAIL("torj_plasma_create_from_data: grid or profile too small");
+    if ((double)(g->nR + 2) * (double)(g->nZ + 2) >= 2147483648.0) FAIL("torj_plasma_create_from_data: grid too large (2^31 nodes)");
     for (int i = 1; i < n_prof; ++i) if (!(psi_prof[i] > psi_prof[i - 1])) FAIL("torj_plasma_create_from_data: psi_prof must increase");
     if (set_device(c)) return 1;
     cudaStream_t st = c->stream;
@@ -532,15 +531,14 @@ int torj_plasma_create_from_data(torj_ctx* c, const torj_grid* g, const double* 
     Guard<torj_plasma, torj_plasma_destroy> guard(p);
     p->ctx = c;
     p->id = ++g_plasma_serial;
-    CK(cudaMalloc(&p->dA, 2 * nodes * sizeof(double2)));
-    CK(cudaMalloc(&p->dB, nodes * sizeof(double2)));
+    CK(cudaMalloc(&p->dA, 3 * nodes * sizeof(double2)));
     k_pack_tables<<<(unsigned)((nodes + 255) / 256), 256, 0, st>>>(d_coef, d_coef + nodes, d_coef + 2 * nodes, d_coef + 3 * nodes,
-                                                                 d_coef + 4 * nodes, d_coef + 5 * nodes, (long long)nodes, p->dA, p->dB);
+                                                                 d_coef + 4 * nodes, d_coef + 5 * nodes, (long long)nodes, p->dA);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     DevTables& T = p->T;
-    T.A = p->dA; T.B = p->dB;
+    T.A = p->dA;
     T.nR = nR; T.nZ = nZ; T.row = sr;
     T.r0 = g->R_first; T.z0 = g->Z_first;
     double hr = (g->R_last - g->R_first) / (double)(nR - 1), hz = (g->Z_last - g->Z_first) / (double)(nZ - 1);
@@ -559,7 +557,6 @@ void torj_plasma_destroy(torj_plasma* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaFree(p->dA);
-    cudaFree(p->dB);
     cudaFree(p->dT);
     delete p;
 }
@@ -964,7 +961,7 @@ int torj_bundle_trace(torj_bundle* b, const torj_plasma* p, const torj_options* 
     size_t smem = (size_t)TORJ_BIN_WORDS(n_psi) * sizeof(double);
     if (model == 1 && lpr == 1) smem += (size_t)TORJ_WARM_H * TORJ_TPB * sizeof(double);
 #if TORJ_K_SMEM
-    smem += (size_t)7 * 7 * TORJ_TPB * sizeof(double);
+    smem += (size_t)TORJ_K_WORDS * sizeof(double);
 #endif
 #if TORJ_PARK
     smem += (size_t)TORJ_PARK_SLOTS * TORJ_TPB * sizeof(double);

@@ -47,8 +47,8 @@ namespace torj {
 #endif
 
 struct DevTables {
-    const double2* __restrict__ A;  // 2 double2 per node
-    const double2* __restrict__ B;  // 1 double2 per node
+    const double2* __restrict__ A;  // 3 double2 per node: (BR, BZ), (Bphi, ln ne), (ln Te, psi) — one table, so that a stencil row is
+                                    // ONE contiguous 192-byte run behind one address (two tables: two address chains per row)
     int nR, nZ, row;                // row = nR + 2 nodes per Z line
     double r0, z0, inv_hr, inv_hz, rlast, zlast;
     double psi_prof_max;
@@ -135,13 +135,14 @@ __device__ __forceinline__ double sqrt_fast(double x) {  // x >= 0
 // ------------------------------------------------------------------------------------------------
 // cubic B-spline weights; dw already divided by the grid step
 // ------------------------------------------------------------------------------------------------
+__constant__ double c_bsk[2] = {1.0 / 6.0, 2.0 / 3.0};  // constant-bank operands: a 64-bit literal costs two MOVs per use
 __device__ __forceinline__ void bs_weights(double d, double inv_h, double w[4], double dw[4]) {
     double e = 1.0 - d;
     double d2 = d * d, e2 = e * e;
-    w[0] = e2 * e * (1.0 / 6.0);
-    w[1] = 2.0 / 3.0 - d2 + 0.5 * d2 * d;
-    w[2] = 2.0 / 3.0 - e2 + 0.5 * e2 * e;
-    w[3] = d2 * d * (1.0 / 6.0);
+    w[0] = e2 * e * c_bsk[0];
+    w[1] = c_bsk[1] - d2 + 0.5 * d2 * d;
+    w[2] = c_bsk[1] - e2 + 0.5 * e2 * e;
+    w[3] = d2 * d * c_bsk[0];
     dw[0] = -0.5 * e2 * inv_h;
     dw[1] = (1.5 * d2 - 2.0 * d) * inv_h;
     dw[2] = (2.0 * e - 1.5 * e2) * inv_h;
@@ -171,8 +172,16 @@ struct Fields {  // value, d/dR, d/dZ
 };
 
 // all five RHS fields (and optionally psi_N) at a point inside the grid
+#ifndef TORJ_TE_PSI_LAZY
+#define TORJ_TE_PSI_LAZY 1  // 1: ln T_e and psi_N (the third double2 of a node) in a second pass over the stencil, taken only by the
+#endif                      //    evaluations that use one of them — the FSAL / seed / callback stages (psi_N) and those that evaluate
+                            //    alpha (T_e): outside the absorbing layer five RHS evaluations of six need neither
+#if TORJ_TE_PSI_LAZY && TORJ_ROLL_STENCIL
+#error "TORJ_TE_PSI_LAZY needs the row weights of the unrolled stencil"
+#endif
 template <bool WITH_PSI>
-__device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true) {
+__device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true,
+                                               bool need_te = true) {
     double wr[4], dwr[4];
     int br = bs_locate(R, T.r0, T.inv_hr, T.nR, wr, dwr);
 #if TORJ_ROLL_STENCIL
@@ -199,22 +208,26 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
 #else
         const double wzj = wz[j], dwzj = dwz[j];
 #endif
-        size_t node = (size_t)(bz + j) * T.row + br;
-        const double2* pa = T.A + 2 * node;
-        const double2* pb = T.B + node;
+        // 32-bit node index (the host refuses grids of 2^31 nodes): one IMAD.WIDE per table and row instead of 64-bit multiplies
+        const unsigned node = (unsigned)((bz + j) * T.row + br);
+        const double2* pa = T.A + 3 * (size_t)node;
         double a[4] = {0, 0, 0, 0}, aR[4] = {0, 0, 0, 0};
+#if !TORJ_TE_PSI_LAZY
         double at = 0.0, ap = 0.0, apR = 0.0;
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double2 q0 = __ldg(pa + 2 * i);
-            double2 q1 = __ldg(pa + 2 * i + 1);
-            double2 q2 = __ldg(pb + i);
+            double2 q0 = __ldg(pa + 3 * i);
+            double2 q1 = __ldg(pa + 3 * i + 1);
             a[0] = fma(wr[i], q0.x, a[0]); aR[0] = fma(dwr[i], q0.x, aR[0]);
             a[1] = fma(wr[i], q0.y, a[1]); aR[1] = fma(dwr[i], q0.y, aR[1]);
             a[2] = fma(wr[i], q1.x, a[2]); aR[2] = fma(dwr[i], q1.x, aR[2]);
             a[3] = fma(wr[i], q1.y, a[3]); aR[3] = fma(dwr[i], q1.y, aR[3]);
+#if !TORJ_TE_PSI_LAZY
+            double2 q2 = __ldg(pa + 3 * i + 2);
             at = fma(wr[i], q2.x, at);
             if (WITH_PSI && (!TORJ_PSI_LAZY || need_psi)) { ap = fma(wr[i], q2.y, ap); apR = fma(dwr[i], q2.y, apR); }
+#endif
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -222,14 +235,33 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
             vR[q] = fma(wzj, aR[q], vR[q]);
             vZ[q] = fma(dwzj, a[q], vZ[q]);
         }
+#if !TORJ_TE_PSI_LAZY
         te = fma(wzj, at, te);
         if (WITH_PSI && (!TORJ_PSI_LAZY || need_psi)) { ps = fma(wzj, ap, ps); psR = fma(wzj, apR, psR); psZ = fma(dwzj, ap, psZ); }
+#endif
 #if TORJ_ROW_FENCE
         // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
         // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
         asm volatile("" ::: "memory");
 #endif
     }
+#if TORJ_TE_PSI_LAZY
+    if (need_te || (WITH_PSI && need_psi)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2* pc = T.A + 3 * (size_t)(unsigned)((bz + j) * T.row + br) + 2;
+            double at = 0.0, ap = 0.0, apR = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 q2 = __ldg(pc + 3 * i);
+                at = fma(wr[i], q2.x, at);
+                if (WITH_PSI) { ap = fma(wr[i], q2.y, ap); apR = fma(dwr[i], q2.y, apR); }
+            }
+            te = fma(wz[j], at, te);
+            if (WITH_PSI) { ps = fma(wz[j], ap, ps); psR = fma(wz[j], apR, psR); psZ = fma(dwz[j], ap, psZ); }
+        }
+    }
+#endif
     f.BR = v[0]; f.BR_R = vR[0]; f.BR_Z = vZ[0];
     f.BZ = v[1]; f.BZ_R = vR[1]; f.BZ_Z = vZ[1];
     f.Bp = v[2]; f.Bp_R = vR[2]; f.Bp_Z = vZ[2];
@@ -258,10 +290,10 @@ __device__ __noinline__ Ext3 eval_field_ext(const DevTables T, int field, double
             size_t node = (size_t)(bz + j) * T.row + br + i;
             double c;
             if (field < 4) {
-                double2 q = __ldg(T.A + 2 * node + (field >> 1));
+                double2 q = __ldg(T.A + 3 * node + (field >> 1));
                 c = (field & 1) ? q.y : q.x;
             } else {
-                double2 q = __ldg(T.B + node);
+                double2 q = __ldg(T.A + 3 * node + 2);
                 c = (field == 4) ? q.x : q.y;
             }
             a = fma(wr[i], c, a);
@@ -283,9 +315,10 @@ __device__ __forceinline__ bool inside_grid(const DevTables& T, double R, double
 }
 
 template <bool WITH_PSI>
-__device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true) {
+__device__ __forceinline__ void eval_fields(const DevTables& T, double R, double Z, Fields& f, bool need_psi = true,
+                                            bool need_te = true) {
     if (inside_grid(T, R, Z)) {
-        eval_fields_in<WITH_PSI>(T, R, Z, f, need_psi);
+        eval_fields_in<WITH_PSI>(T, R, Z, f, need_psi, need_te);
     } else {
         Ext3 e;
         e = eval_field_ext(T, 0, R, Z); f.BR = e.v; f.BR_R = e.dR; f.BR_Z = e.dZ;
@@ -311,11 +344,11 @@ __device__ __forceinline__ void eval_psi(const DevTables& T, double R, double Z,
     double s = 0, sR = 0, sZ = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const double2* pb = T.B + (size_t)(bz + j) * T.row + br;
+        const double2* pb = T.A + 3 * ((size_t)(bz + j) * T.row + br) + 2;
         double a = 0, aR = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double c = __ldg(pb + i).y;
+            double c = __ldg(pb + 3 * i).y;
             a = fma(wr[i], c, a);
             aR = fma(dwr[i], c, aR);
         }
@@ -443,24 +476,58 @@ __device__ const double d_exp_tab[64] = {
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951,
 };
+#ifndef TORJ_EXP_SMEM
+#define TORJ_EXP_SMEM 1  // 1: the 2^(j/64) table is read from shared memory (LDS behind a 32-bit address: 3 instructions instead of
+#endif                   //    5 for the 64-bit global address; 99.0 -> 95.6 ms, alpha_floor = 0: 215.9 -> 197.8). EVERY kernel that
+                         //    reaches exp_fast must call exp_tab_init() first
+__device__ __forceinline__ double* exp_tab_smem() {
+    __shared__ double tab[64];
+    return tab;
+}
+__device__ __forceinline__ void exp_tab_init() {  // whole block, before any early return
+#if TORJ_EXP_SMEM && TORJ_EXP_TABLE
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) exp_tab_smem()[j] = d_exp_tab[j];
+    __syncthreads();
+#endif
+}
+__constant__ double c_expt[6] = {92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+// NEG: the caller's argument cannot exceed +708 (an integrand exp(-mu (gamma - 1) ...)): only the underflow side is clamped
+template <bool NEG = false>
 __device__ __forceinline__ double exp_fast(double x) {
-    x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
-    x = x > 708.0 ? 708.0 : x;
 #if TORJ_EXP_TABLE
     {
-        // n = rint(64 x / ln2) = 64 k + j ; r = x - n ln2/64 (|r| <= ln2/128: r^6/720 < 4e-17) ; exp(x) = 2^k 2^(j/64) p(r)
-        const double nd = rint(x * 92.33248261689366);
-        double r = fma(nd, -0.01083042469326756, x);
-        r = fma(nd, -2.9815858269852933e-12, r);
-        const int n = (int)nd;
-        const double t = __ldg(d_exp_tab + (n & 63));
-        double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-        p = fma(p, r, 1.0 / 6.0);
+        // 22-24 instructions (29 before this arrangement). An FP64 instruction takes ONE operand that is not a register: a
+        // constant-bank word or an immediate that fits the high word; everything else costs MOVs — hence mul + add pairs
+        // where a fused form would need two constants.
+        // |x| > 708 -> +-708 (NaN stays NaN): the high word is replaced, the low word kept (|x| < 708.0005)
+        const int hi = __double2hiint(x);
+        int hic;
+        if (NEG) hic = (x < -708.0) ? (int)0xC0862000 : hi;
+        else hic = (fabs(x) > 708.0) ? (0x40862000 | (hi & 0x80000000)) : hi;
+        x = __hiloint2double(hic, __double2loint(x));
+        // n = rint(64 x / ln2) = 64 k + j in the low word of t (1.5 2^52 trick: no conversion instructions);
+        // r = x - n ln2/64 (|r| <= ln2/128) ; exp(x) = 2^k 2^(j/64) (1 + expm1(r))
+        const double t = __dadd_rn(__dmul_rn(x, c_expt[0]), 6755399441055744.0);
+        const int n = __double2loint(t);
+        const double nd = t - 6755399441055744.0;
+        double r = fma(nd, c_expt[1], x);
+        r = fma(nd, c_expt[2], r);
+#if TORJ_EXP_SMEM
+        const double tb = exp_tab_smem()[n & 63];
+#else
+        const double tb = __ldg(d_exp_tab + (n & 63));
+#endif
+        // expm1(r) = r + r^2 (1/2 + r (1/6 + r (1/24 + r/120)))
+        double p = __dadd_rn(__dmul_rn(r, c_expt[3]), c_expt[4]);
+        p = fma(p, r, c_expt[5]);
         p = fma(p, r, 0.5);
-        const double q = fma(p * r, r, r);  // expm1(r): t + t q rounds once (worst 1.3 ulp against 2.2 for t * (1 + q))
-        return fma(t, q, t) * __hiloint2double(((n >> 6) + 1023) << 20, 0);
+        const double q = fma(p * r, r, r);
+        const double v = fma(tb, q, tb);  // in (0.99, 2): t + t q rounds once (worst 1.3 ulp); the result is normal for |x| <= 708
+        return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
     }
 #endif
+    x = x < -708.0 ? -708.0 : x;  // plain selects: fmin/fmax carry NaN handling that costs ~10 instructions each
+    x = x > 708.0 ? 708.0 : x;
     const double kd = rint(x * c_exp[0]);
     double r = fma(kd, c_exp[1], x);
     r = fma(kd, c_exp[2], r);
@@ -532,7 +599,7 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
         const bool pos = et >= 0.0;
         const double exa = c.eb * (pos ? big : small), exb = c.eb * (pos ? small : big);
 #else
-        const double exa = exp_fast(c.e0 + et), exb = exp_fast(c.e0 - et);
+        const double exa = exp_fast<true>(c.e0 + et), exb = exp_fast<true>(c.e0 - et);
 #endif
         const double z = c.x_m * sq;
         double J, D;
@@ -767,7 +834,8 @@ __device__ __forceinline__ void rhs(const DevTables& T, const RayConst& rc, cons
     const double R = R2 * iR;
     const double c = x * iR, s = y * iR;
     Fields f;
-    eval_fields<WITH_PSI>(T, R, z, f, need_psi);
+    // ln T_e feeds alpha only (and the probes): not needed where alpha is skipped
+    eval_fields<WITH_PSI>(T, R, z, f, need_psi, (WITH_ALPHA && !skip_alpha) || ain != nullptr || pv != nullptr);
     const double B2 = f.BR * f.BR + f.Bp * f.Bp + f.BZ * f.BZ;
     const double iB = rsqrt_fast(B2);
     const double Babs = B2 * iB;

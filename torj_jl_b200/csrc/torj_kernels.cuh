@@ -139,6 +139,7 @@ __device__ inline void refraction_equations(const double N[3], double X, double 
 }
 
 __global__ void k_ray_init(DevTables T, BundleDev B, SolverOpts O) {
+    exp_tab_init();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.n_rays) return;
     const long long n = B.n_rays;
@@ -298,6 +299,13 @@ __device__ __forceinline__ double rms7(const double v[7]) {
     return sqrt(s / 7.0);
 }
 
+// Final position outside the grid? Out of line on purpose: inlined, the compiler hoisted the side-effect-free sqrt(x^2 + y^2)
+// out of the retirement branch and ran it on EVERY trip (20 instructions, 2.2 % of the kernel's stall samples in ncu).
+__device__ __noinline__ bool left_grid(double r0, double rlast, double z0, double zlast, double x, double y, double z) {
+    const double R = sqrt(x * x + y * y);
+    return !(R >= r0 && R <= rlast && z >= z0 && z <= zlast);
+}
+
 // pow() expands to ~150 instructions with slow paths; the controller needs it only on rejected / shrinking steps,
 // so one out-of-line copy keeps the hot loop small
 __device__ __noinline__ double pow_nl(double x, double y) { return pow(x, y); }
@@ -314,7 +322,11 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 #define TORJ_SMEM_BINS 0  // 1: single-profile bundles book into block-local shared-memory bins flushed at the end (round 1).
 #endif                    //    Measured SLOWER than booking straight into global memory (119.6 against 117.8 ms on the 65 543-ray
                           //    beam): a shared-memory FP64 atomicAdd is a CAS loop, a global one is a fire-and-forget RED.ADD.F64.
-#define TORJ_BIN_WORDS(n_psi) (TORJ_SMEM_BINS ? (n_psi) : 0)
+#define TORJ_BIN_WORDS(n_psi) (TORJ_SMEM_BINS ? (((n_psi) + 1) & ~1) : 0)
+#ifndef TORJ_K_PAIRS
+#define TORJ_K_PAIRS 1  // 1 (with TORJ_K_SMEM): stage derivatives stored as 4 double2 per stage and thread (8th slot unused), so a
+#endif                  //    stage is read with 4 LDS.128 instead of 7 LDS.64
+#define TORJ_K_WORDS ((TORJ_K_PAIRS ? 56 : 49) * TORJ_TPB)  // doubles of stage storage per CTA
 #ifndef TORJ_K_SMEM
 #define TORJ_K_SMEM 1  // 1: Runge-Kutta stage derivatives k[S][7] live in shared memory instead of (L1-backed) local memory
 #endif
@@ -367,17 +379,23 @@ enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT 
 //   whose alpha costs ~100x the rest of the RHS.
 template <int SCH, bool HIGH = false, int MODEL = 0, int LPR = 1>
 __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
+    exp_tab_init();
     constexpr bool COOP = LPR == 32;
     constexpr int S = Scheme<SCH>::S;
     constexpr int ORDER = Scheme<SCH>::ORDER;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
 #if TORJ_SMEM_BINS
     double* s_bins = smem;                                 // [n_psi] block-local deposition bins
 #endif
     const double* __restrict__ s_edges = a.psi_edges;      // psi levels: read-only, through L1 (__ldg)
 #if TORJ_K_SMEM
+#if TORJ_K_PAIRS
+    double* ks = smem + TORJ_BIN_WORDS(a.n_psi) + 2 * threadIdx.x;         // KK(j, 2p + q) at ks[(j*4+p)*2*TORJ_TPB + q]: 16-byte pairs
+#define KK(j, i) ks[((j) * 4 + ((i) >> 1)) * 2 * TORJ_TPB + ((i) & 1)]
+#else
     double* ks = smem + TORJ_BIN_WORDS(a.n_psi) + threadIdx.x;             // KK(j, i) at ks[(j*7+i)*TORJ_TPB]: conflict-free
 #define KK(j, i) ks[((j) * 7 + (i)) * TORJ_TPB]
+#endif
 #else
     double k_loc[S][7];
 #define KK(j, i) k_loc[j][i]
@@ -420,7 +438,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     // sits at the 255-register limit and the compiler, not knowing trip frequencies, otherwise spills values that
     // every RHS evaluation touches (ray constants, counters) to local memory (122 -> 72 bytes of spills, -1 % time;
     // parking the once-per-step scalars as well removes the spills altogether but gains nothing more).
-    double* pk = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + threadIdx.x;
+    double* pk = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? TORJ_K_WORDS : 0) + threadIdx.x;
 #define PK(k) pk[(k) * TORJ_TPB]
     long long& ray = *reinterpret_cast<long long*>(&PK(0));
     long long& tj = *reinterpret_cast<long long*>(&PK(1));  // index into the trajectory window or -1
@@ -444,7 +462,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
     unsigned int rays_ok = 0;
 #endif
     // warm model, one ray per lane: shared-memory slots where a lane's quadrature sums wait for the serial solve
-    double* wstash = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? 49 * TORJ_TPB : 0) + (TORJ_PARK ? TORJ_PARK_SLOTS * TORJ_TPB : 0) + threadIdx.x;
+    double* wstash = smem + TORJ_BIN_WORDS(a.n_psi) + (TORJ_K_SMEM ? TORJ_K_WORDS : 0) + (TORJ_PARK ? TORJ_PARK_SLOTS * TORJ_TPB : 0) + threadIdx.x;
     int phase = PH_IDLE, st = 0;
     bool exhausted = false;
     double u[7], tmp[7];
@@ -614,6 +632,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
         // <= 4 idle trips per segment, but measured +1.5 %: the fixed cadence is also what regroups stragglers.)
         const bool aligned = (cadence == 0);
         cadence = (cadence + 1 == S - 1) ? 0 : cadence + 1;
+        // (wrapping the refill logic below into one vote over "some lane is not busy" measured neutral to slower: 99.2 against 99.0)
         if (a.interleave && phase == PH_WAIT && aligned) {
             if (own) phase = PH_RESUME;  // continuation: the state is here
             else start_item(ray);
@@ -654,12 +673,12 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
         // ---- the one RHS evaluation of this trip (reference src/solve.jl:85-95), warp-converged
         double out[9];
+        const bool inner = (phase == PH_STAGE && st < S - 1);  // an inner Runge-Kutta stage: five trips of six
         // alpha is evaluated in full at the FSAL stage (= first stage of the next step) and in the seed / callback /
         // initial-dt phases; the inner stages take alpha = 0 when that evaluation found every harmonic negligible
         // with a 1e10 margin (abs_albajar)
         if (MODEL == 0) {
             if (phase >= PH_SEED) {
-                const bool inner = (phase == PH_STAGE && st < S - 1);
                 rhs<true, true, HIGH, LPR>(T, rc, tmp, out, cnt, nullptr, inner && a_skip, &a_skip_next, nullptr,
                                             !inner && phase != PH_INITDT);  // psi_N is used at the FSAL / seed / callback stages only
                 if (!inner) a_skip = a_skip_next;
@@ -669,7 +688,6 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             AlphaIn ain;
             ain.X = 0.1; ain.Y = 0.5; ain.N2 = 1.0; ain.Np = 0.0; ain.lnTe = -1e300; ain.inorm = 1.0;
             const bool evaluated = phase >= PH_SEED;
-            const bool inner = (phase == PH_STAGE && st < S - 1);
             if (evaluated) rhs<false, true, false, false>(T, rc, tmp, out, cnt, nullptr, false, nullptr, &ain, !inner && phase != PH_INITDT);
             const bool want = evaluated && !(inner && a_skip);
             if (evaluated && !want) cnt.n_askip++;
@@ -682,56 +700,37 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 
         // ---- phase bookkeeping
         int act = ACT_NONE;
-        if (phase == PH_SEED) {
-            // derivative at entry (FSAL seed), psi there, and the vacuum leg launch -> entry (P = 1, straight line)
+        // (the common case first and on its own predicate: a ladder over the phases costs three compare-and-branch per trip)
+        if (inner) {
+            {
 #pragma unroll
-            for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
-            psi_cur = out[7];
-            dpsi_cur = out[8];
-            double psl = a.B.psi_launch[ray];
-            dst.shell = locate_shell(s_edges, n_psi, psl);
-            dst.valid = 0; dst.P_last = 1.0;
-            double dlin = (psi_cur - psl) / s0;
-            depo_step(dst, s_edges, n_psi, s0, psl, psi_cur, dlin, dlin, 1.0, 1.0, 0.0, 0.0, sink);
-            act = ACT_BEGIN_SEGMENT;
-        } else if (phase == PH_INITDT) {
-            // second half of OrdinaryDiffEq's ode_determine_initdt (Hairer): out = f(u + dt0 f0)
-            double v[7];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) v[i] = (out[i] - KK(0, i)) / (O.abstol + fabs(u[i]) * O.reltol);
-            double d2 = rms7(v) / dt0;
-            double md = fmax(d1, d2);
-            // 10^(-(2 + log10 md)/order) = (100 md)^(-1/order)
-            // dt1 = 10^(-(2 + log10 md)/order) = (100 md)^(-1/order) >= dtmax  <=>  100 md <= dtmax^-order: the usual
-            // case (dt = dtmax) needs no pow()
-            if (md > 1e-15 && 100.0 * md <= dtmax_pow && 100.0 * dt0 >= O.dtmax) {
-                dt = O.dtmax;
-            } else {
-                double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow_nl(100.0 * md, -1.0 / (double)ORDER);
-                dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
-            }
-            act = ACT_BEGIN_STEP;
-        } else if (phase == PH_STAGE) {
-#pragma unroll
-            for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
-            if (st < S - 1) {
+                for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
                 st++;
                 // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
                 // stale slots hold finite values of the previous step, so the trip count is lane-independent
-                double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                double acc[7];
+                {
+                    const double a0 = s_a[st][0];  // st >= 2 here: the first term initialises the sums
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) acc[i] = a0 * KK(0, i);
+                }
 #if TORJ_ROLL_J
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-                for (int j = 0; j < ((TORJ_ST_BOUND && TORJ_ROLL_J) ? st : S - 1); ++j) {
+                for (int j = 1; j < ((TORJ_ST_BOUND && TORJ_ROLL_J) ? st : S - 1); ++j) {
                     const double aj = s_a[st][j];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) acc[i] = fma(aj, KK(j, i), acc[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < 7; ++i) tmp[i] = fma(dt, acc[i], u[i]);
-            } else {
+            }
+        } else if (phase == PH_STAGE) {
+            {
+#pragma unroll
+                for (int i = 0; i < 7; ++i) KK(st, i) = out[i];
                 // tmp is the proposed new state (FSAL); embedded error estimate (err = sum_j btilde_j k_j, accumulated
                 // stage by stage) and PI controller
                 psi_new = out[7];
@@ -807,6 +806,35 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                     }
                 }
             }
+        } else if (phase == PH_SEED) {
+            // derivative at entry (FSAL seed), psi there, and the vacuum leg launch -> entry (P = 1, straight line)
+#pragma unroll
+            for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
+            psi_cur = out[7];
+            dpsi_cur = out[8];
+            double psl = a.B.psi_launch[ray];
+            dst.shell = locate_shell(s_edges, n_psi, psl);
+            dst.valid = 0; dst.P_last = 1.0;
+            double dlin = (psi_cur - psl) / s0;
+            depo_step(dst, s_edges, n_psi, s0, psl, psi_cur, dlin, dlin, 1.0, 1.0, 0.0, 0.0, sink);
+            act = ACT_BEGIN_SEGMENT;
+        } else if (phase == PH_INITDT) {
+            // second half of OrdinaryDiffEq's ode_determine_initdt (Hairer): out = f(u + dt0 f0)
+            double v[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) v[i] = (out[i] - KK(0, i)) / (O.abstol + fabs(u[i]) * O.reltol);
+            double d2 = rms7(v) / dt0;
+            double md = fmax(d1, d2);
+            // 10^(-(2 + log10 md)/order) = (100 md)^(-1/order)
+            // dt1 = 10^(-(2 + log10 md)/order) = (100 md)^(-1/order) >= dtmax  <=>  100 md <= dtmax^-order: the usual
+            // case (dt = dtmax) needs no pow()
+            if (md > 1e-15 && 100.0 * md <= dtmax_pow && 100.0 * dt0 >= O.dtmax) {
+                dt = O.dtmax;
+            } else {
+                double dt1 = (md <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow_nl(100.0 * md, -1.0 / (double)ORDER);
+                dt = fmin(fmin(100.0 * dt0, dt1), O.dtmax);
+            }
+            act = ACT_BEGIN_STEP;
         } else if (phase == PH_CALLBACK) {
 #pragma unroll
             for (int i = 0; i < 7; ++i) KK(0, i) = out[i];
@@ -817,7 +845,11 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
             act = ACT_BEGIN_SEGMENT;
         }
 
-        // ---- transitions that need no RHS evaluation
+        // ---- transitions that need no RHS evaluation. The blocks stand in the order of the chain accept -> next step ->
+        // segment end -> next segment, so one pass handles every case but one (a fresh segment that skips its initial-dt probe
+        // goes back to the step block); as an else-if ladder inside the loop every link of the chain cost a loop trip
+        // (five trips of six no lane of a warp in step has a transition: one vote skips the whole ladder)
+        if (__any_sync(FULL, act != ACT_NONE))
         while (act != ACT_NONE) {
             if (act == ACT_AFTER_ACCEPT) {
                 put_point(t, u, u[6], -KK(0, 6));  // dP/ds sample = P*alpha (reference src/solve.jl:171)
@@ -826,26 +858,31 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 psi_cur = psi_new; dpsi_cur = dpsi_new;
                 dt = fmin(O.dtmax, dtnew);
                 act = ACT_BEGIN_STEP;
-            } else if (act == ACT_BEGIN_STEP) {
-                if (!(t < tstop)) { act = ACT_END_SEGMENT; continue; }
-                if (++nstep > O.max_steps) { rstat = 4; act = ACT_END_SEGMENT; continue; }  // TORJ_RAY_MAX_STEPS
-                dt = fmin(dt, tstop - t);
-                st = 1;
-                {
+            }
+            if (act == ACT_BEGIN_STEP) {
+                if (!(t < tstop)) {
+                    act = ACT_END_SEGMENT;
+                } else if (++nstep > O.max_steps) {
+                    rstat = 4;  // TORJ_RAY_MAX_STEPS
+                    act = ACT_END_SEGMENT;
+                } else {
+                    dt = fmin(dt, tstop - t);
+                    st = 1;
                     const double a10 = dt * s_a[1][0];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
                         const double k0 = KK(0, i);
                         tmp[i] = fma(a10, k0, u[i]);
                     }
+                    phase = PH_STAGE;
+                    act = ACT_NONE;
                 }
-                phase = PH_STAGE;
-                act = ACT_NONE;
-            } else if (act == ACT_END_SEGMENT) {
+            }
+            if (act == ACT_END_SEGMENT) {
                 // termination tests at the segment end (reference src/solve.jl:174-176) and retirement
                 bool done = TORJ_FATAL(rstat) || seg >= O.n_segments || psi_cur > O.psi_stop || u[6] < O.p_stop;
                 if (done) {
-                    if (rstat == 0 && !inside_grid(T, sqrt(u[0] * u[0] + u[1] * u[1]), u[2])) rstat = 3;  // TORJ_RAY_LEFT_GRID
+                    if (rstat == 0 && left_grid(T.r0, T.rlast, T.z0, T.zlast, u[0], u[1], u[2])) rstat = 3;  // TORJ_RAY_LEFT_GRID
                     last_stat = rstat;
                     if (writer) {
                         a.B.status[ray] = rstat;
@@ -893,7 +930,8 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 } else {
                     act = ACT_BEGIN_SEGMENT;
                 }
-            } else {  // ACT_BEGIN_SEGMENT: one fresh ODEProblem of the reference (src/solve.jl:155-161)
+            }
+            if (act == ACT_BEGIN_SEGMENT) {  // one fresh ODEProblem of the reference (src/solve.jl:155-161)
                 seg++;
                 t = (double)(seg - 1) * s_step + s0;
                 tstop = (double)seg * s_step + s0;
@@ -967,6 +1005,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
 // the stencil loads and the absorbing layer coherent (a random ray order costs 40 %).
 __global__ void k_predict_life(DevTables T, BundleDev B, SolverOpts O, double harm_cost, int* __restrict__ life,
                                int* __restrict__ lmax) {
+    exp_tab_init();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: warp = ray block
     const long long n = B.n_rays;
     double cost = 1.0;
@@ -1015,7 +1054,8 @@ __global__ void k_finalize(const double* bins, const double* dV, int n_psi, int 
 // model: 0 Albajar, 1 warm-plasma (needs 19 * blockDim doubles of dynamic shared memory; whole warps take part)
 __global__ void k_probe(DevTables T, long long n, const double* x, const double* N, double f, int mode, double te_min,
                         int max_harmonic, double alpha_floor, int model, const double2* warm_tab, double* out) {
-    extern __shared__ double smem[];
+    exp_tab_init();
+    extern __shared__ __align__(16) double smem[];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     if (!active) i = n - 1;
@@ -1043,7 +1083,8 @@ __global__ void k_probe(DevTables T, long long n, const double* x, const double*
 
 __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int mode, double te_min, int max_harmonic,
                       double alpha_floor, int model, const double2* warm_tab, double* du) {
-    extern __shared__ double smem[];
+    exp_tab_init();
+    extern __shared__ __align__(16) double smem[];
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     if (!active) i = n - 1;
@@ -1067,6 +1108,7 @@ __global__ void k_rhs(DevTables T, long long n, const double* u, double f, int m
 // probe). in[7][n]: omega, X, Y, N_r, theta, te, v_g_perp; out[5][n]: N_warm, alpha, lrm, ierr, iterations.
 // One point per lane; the warp does the quadratures one after the other, the owner finishes its own.
 __global__ void k_warm_alpha(long long n, const double* in, int imod, const double2* warm_tab, double* out) {
+    exp_tab_init();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     if (!active) i = n - 1;
@@ -1181,12 +1223,12 @@ __global__ void k_profile_to_grid(const double* __restrict__ psi_nodes, long lon
 
 // six coefficient tables -> the interleaved node layout of DevTables
 __global__ void k_pack_tables(const double* psi, const double* lnne, const double* lnTe, const double* BR, const double* BZ,
-                              const double* Bp, long long nodes, double2* A, double2* B) {
+                              const double* Bp, long long nodes, double2* A) {
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nodes) return;
-    A[2 * k] = make_double2(BR[k], BZ[k]);
-    A[2 * k + 1] = make_double2(Bp[k], lnne[k]);
-    B[k] = make_double2(lnTe[k], psi[k]);
+    A[3 * k] = make_double2(BR[k], BZ[k]);
+    A[3 * k + 1] = make_double2(Bp[k], lnne[k]);
+    A[3 * k + 2] = make_double2(lnTe[k], psi[k]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1278,6 +1320,7 @@ __global__ void k_dfma_latency(int iters, double seed, double* out, long long* c
 
 // the kernel's own elementary functions on n arguments (accuracy tests): out[0..3][n] = rcp, rsqrt, sqrt, exp
 __global__ void k_math_probe(long long n, const double* x, double* out) {
+    exp_tab_init();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
