@@ -6,10 +6,11 @@
 //   Albajar absorption           <- reference src/absorption.jl:10-64,132-235
 //   streaming psi-shell deposit  <- reference src/plasma.jl:91-151 (see DESIGN.md for the algorithm and its bound)
 //
-// Table layout in HBM (one node = one (R,Z) B-spline coefficient position, R fastest):
-//   tabA[node] = { (B_R, B_Z), (B_phi, ln n_e) }   2 x double2   fields whose gradients the RHS needs
-//   tabB[node] = { ln T_e, psi_N }                 1 x double2   value-only field + the deposition field
-// so a 4x4 stencil is 4 contiguous runs of 128 B (A) and 64 B (B), read with 16-byte __ldg loads.
+// Table layout in HBM (one node = one (R,Z) B-spline coefficient position, R fastest), ONE table of 3 double2 per node:
+//   tab[node] = { (B_R, B_Z), (B_phi, ln n_e), (ln T_e, psi_N) }
+// The first two pairs carry the fields whose gradients every RHS needs; the third (a value-only field and the deposition
+// field) is read in a second pass, only by the evaluations that use it. A 4x4 stencil is 4 contiguous runs of 192 B behind
+// one address each, read with 16-byte __ldg loads.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>

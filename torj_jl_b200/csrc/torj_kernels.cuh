@@ -361,6 +361,27 @@ template <> struct Scheme<1> { static constexpr int S = 4; static constexpr int 
 enum { PH_IDLE = 0, PH_WAIT = 1, PH_RESUME = 2, PH_SEED = 3, PH_INITDT = 4, PH_STAGE = 5, PH_CALLBACK = 6 };
 enum { ACT_NONE = 0, ACT_BEGIN_SEGMENT = 1, ACT_BEGIN_STEP = 2, ACT_END_SEGMENT = 3, ACT_AFTER_ACCEPT = 4 };
 
+#ifndef TORJ_STAGE_SWITCH
+#define TORJ_STAGE_SWITCH 0  // 1: the stage combination as a switch over the stage with exact-length unrolled sums and
+#endif                       //    constant-bank coefficients (no loop control, no coefficient loads), at +250 static instructions
+#if TORJ_K_PAIRS
+#define TORJ_KK_AT(ks, j, i) (ks)[((j) * 4 + ((i) >> 1)) * 2 * TORJ_TPB + ((i) & 1)]
+#else
+#define TORJ_KK_AT(ks, j, i) (ks)[((j) * 7 + (i)) * TORJ_TPB]
+#endif
+template <int SCH, int ST>
+__device__ __forceinline__ void stage_sum_unrolled(const double* ks, double dt, const double* u, double* tmp) {
+    double acc[7];
+#pragma unroll
+    for (int j = 0; j < ST; ++j) {
+        const double aj = c_tab[SCH].a[ST][j];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) acc[i] = j == 0 ? aj * TORJ_KK_AT(ks, 0, i) : fma(aj, TORJ_KK_AT(ks, j, i), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tmp[i] = fma(dt, acc[i], u[i]);
+}
+
 #ifdef TORJ_MAXNREG
 #define TORJ_TRACE_BOUNDS __maxnreg__(TORJ_MAXNREG)
 #else
@@ -708,6 +729,15 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 st++;
                 // u + dt * sum_j a[st][j] k_j over ALL S-1 earlier slots: the tableau rows are zero-padded and
                 // stale slots hold finite values of the previous step, so the trip count is lane-independent
+#if TORJ_STAGE_SWITCH && TORJ_K_SMEM
+                switch (st) {
+                    case 2: stage_sum_unrolled<SCH, 2>(ks, dt, u, tmp); break;
+                    case 3: stage_sum_unrolled<SCH, 3>(ks, dt, u, tmp); break;
+                    case 4: stage_sum_unrolled<SCH, (S > 4 ? 4 : 2)>(ks, dt, u, tmp); break;
+                    case 5: stage_sum_unrolled<SCH, (S > 5 ? 5 : 2)>(ks, dt, u, tmp); break;
+                    default: stage_sum_unrolled<SCH, (S > 6 ? 6 : 2)>(ks, dt, u, tmp); break;
+                }
+#else
                 double acc[7];
                 {
                     const double a0 = s_a[st][0];  // st >= 2 here: the first term initialises the sums
@@ -726,6 +756,7 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 }
 #pragma unroll
                 for (int i = 0; i < 7; ++i) tmp[i] = fma(dt, acc[i], u[i]);
+#endif
             }
         } else if (phase == PH_STAGE) {
             {
@@ -739,9 +770,13 @@ __global__ void TORJ_TRACE_BOUNDS k_trace(TraceArgs a) {
                 bool bad = false;
 #if TORJ_ROLL_J
                 double utv[7] = {0, 0, 0, 0, 0, 0, 0};
+#if TORJ_STAGE_SWITCH
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                 for (int j = 0; j < S; ++j) {
-                    const double bj = s_bt[j];
+                    const double bj = TORJ_STAGE_SWITCH ? c_tab[SCH].bt[j] : s_bt[j];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) utv[i] = fma(bj, KK(j, i), utv[i]);
                 }
