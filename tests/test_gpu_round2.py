@@ -506,3 +506,53 @@ def test_config4_full_sweep_rays_and_whole_beams(gpu_full, oracle_full, gl24):
         assert abs(dep[b] - rb["deposited_power"]) <= FRAC_TOL * max(rb["deposited_power"], 1e-3)
         if rb["deposited_power"] > 1e-6:
             assert l2rel(dP[b], rb["dP_dV"]) < L2_FAITHFUL and l2rel(dP[b], rb["dP_dV_streaming"]) < L2_LIKE
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ray initialisation against its DEFINITIONS — the oracle restates the same algorithm ("weak" 1)
+# ------------------------------------------------------------------------------------------------------------------
+def test_ray_init_obeys_its_definitions_without_the_oracle(gpu_full, arrays_full, launcher):
+    """reference src/solve.jl:18-74, checked on properties instead of on the oracle's restatement: (i) the plasma entry lies on
+    the launch line where psi_N = psi_prof_max (bisection tolerance 1e-6, moved inside, :28-37); (ii) the refracted N is a
+    root of the dispersion relation there (Lambda = 0, :85-89) and (iii) keeps the component of the unit vacuum wave vector
+    tangential to the flux surface (Snell, :45-47). N is read from the state after a 1e-9 m trace."""
+    L = tj.lib()
+    N0 = tj.pol_tor_angles_2_vector(np.deg2rad(27.0), 0.12)
+    pos, dirs, w = tj.launch_peripheral_rays(launcher["x0"], N0, launcher["spot"], launcher["inv_Rc"], launcher["f"])
+    n = len(w)
+    ctx = _lib.context()
+    bh = _lib.c_vp()
+    dp = lambda a: a.ctypes.data_as(_lib.c_dp)
+    posT, dirT = np.ascontiguousarray(pos.T), np.ascontiguousarray(dirs.T)
+    fr, md = np.array([launcher["f"]]), np.array([1], dtype=np.int32)
+    psi = np.linspace(0, 1, 64)
+    opt = tj.default_options(n_segments=1)
+    _lib.check(L.torj_bundle_create(ctx, n, dp(posT), dp(dirT), dp(np.ascontiguousarray(w)), dp(fr), md.ctypes.data_as(_lib.c_ip), 0, C.byref(bh)))
+    try:
+        _lib.check(L.torj_bundle_set_window(bh, 0, n, 8))
+        _lib.check(L.torj_bundle_trace(bh, gpu_full.handle(ctx), C.byref(opt), 1e-9, len(psi), dp(psi)))
+        u = np.zeros((7, n))
+        _lib.check(L.torj_bundle_final_state(bh, dp(u), None, None, None))
+        ts = np.zeros((n, 8)); txyz = np.zeros((n, 3, 8))
+        _lib.check(L.torj_bundle_trajectories(bh, dp(ts), dp(txyz), None, None, None))
+        st = np.zeros(n, dtype=np.int32)
+        _lib.check(L.torj_bundle_results(bh, None, None, None, None, None, st.ctypes.data_as(_lib.c_ip), None))
+    finally:
+        L.torj_bundle_destroy(bh)
+    assert (st == 0).all()
+    entry, s0 = txyz[:, :, 1], ts[:, 1]
+    d_hat = dirs / np.linalg.norm(dirs, axis=1)[:, None]
+    assert np.abs(entry - (pos + s0[:, None] * d_hat)).max() < 1e-12                      # (i) on the launch line
+    Nn = u[3:6].T
+    pr = gpu_full.probe(entry, Nn, launcher["f"], 1)
+    psi_max = float(np.max(arrays_full["psi_prof"])) if "psi_prof" in arrays_full else 1.0
+    assert np.all(pr["psi"] <= psi_max + 1e-12) and np.all(pr["psi"] >= psi_max - 5e-6)   # (i) at the profile edge, inside
+    assert np.abs(pr["Lambda"]).max() < 1e-8                                              # (ii) a root of the dispersion relation
+    h = 1e-6                                                                              # (iii) Snell: grad psi by central differences
+    g = np.stack([(gpu_full.probe(entry + h * e, Nn, launcher["f"], 1)["psi"] - gpu_full.probe(entry - h * e, Nn, launcher["f"], 1)["psi"]) / (2 * h)
+                  for e in np.eye(3)], axis=1)
+    nh = g / np.linalg.norm(g, axis=1)[:, None]
+    tang = lambda v: v - np.sum(v * nh, axis=1)[:, None] * nh
+    assert np.abs(tang(Nn) - tang(d_hat)).max() < 1e-6
+    assert np.all(np.sum(Nn * nh, axis=1) * np.sum(d_hat * nh, axis=1) > 0)               # same side of the surface
+    assert np.all(np.linalg.norm(Nn, axis=1) <= 1.0)                                      # below the cut-off density: N <= 1

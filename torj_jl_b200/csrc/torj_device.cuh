@@ -242,7 +242,7 @@ __device__ __forceinline__ void eval_fields_in(const DevTables& T, double R, dou
 #endif
 #if TORJ_ROW_FENCE
         // keep the 12 loads of the next stencil row from being hoisted above this row's arithmetic: the compiler
-        // otherwise issues all 48 LDG.128 first and holds 192 registers of loads in flight
+        // otherwise issues all 32 LDG.128 first and holds 128 registers of loads in flight
         asm volatile("" ::: "memory");
 #endif
     }
@@ -456,7 +456,7 @@ __device__ __forceinline__ double abs_Al_N_with_pol_vec(double X, double Y, doub
 __constant__ double c_exp[17];  // log2(e), -ln2_hi, -ln2_lo, 1/13!, 1/12!, ..., 1/2!, 1, 1 (constant-bank operands: a
                                 // 64-bit literal costs two extra issue slots per use, a c[][] operand none)
 #ifndef TORJ_EXP_TABLE
-#define TORJ_EXP_TABLE 1  // 1: exp from a 64-entry table of 2^(j/64) (L1-resident) and a degree-5 polynomial instead of degree 13
+#define TORJ_EXP_TABLE 1  // 1: exp from a 64-entry table of 2^(j/64) (in shared memory, TORJ_EXP_SMEM) and a degree-5 polynomial instead of degree 13
                           //    (worst 1.3 ulp; 119.6 -> 118.5 ms on the headline bundle, 253 -> 242 ms with alpha_floor = 0)
 #endif
 __device__ const double d_exp_tab[64] = {
@@ -595,7 +595,7 @@ __device__ __forceinline__ double harmonic_sum(const HarmCoef& c, int m_rt = M) 
 #if TORJ_PAIR_EXP
         // exp(e0 +- et) = eb * exp(+-et - |e1|): the larger factor from one exp, the smaller one as exp(-2|e1|) / larger.
         // (c2 = 0 when it would underflow: the smaller term is then < 1e-150 of the larger one.)
-        const double big = exp_fast(fabs(et) - c.ae1);
+        const double big = exp_fast<true>(fabs(et) - c.ae1);
         const double small = c.c2 * rcp_fast(big);
         const bool pos = et >= 0.0;
         const double exa = c.eb * (pos ? big : small), exb = c.eb * (pos ? small : big);
