@@ -36,6 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GRID, N_PSI, N_GL, S_MAX = 257, 1000, 24, 1.0
+# config5: the beams of a scan differ in cost by frequency and temperature (whole beams per rank left the 170 GHz ranks idle while
+# the 110 GHz ranks worked: 0.11 of peak on 8 GPUs against 0.16 on one); rays of one beam cost the same, so warp-sized blocks of
+# every beam go round the ranks. One profile row per beam on every rank, summed by the same all-reduce.
+C5_BLOCK = 32
 WORKLOADS = {
     "beam64k": dict(name="config3_64k_ray_beam", n_rays=65543, N_rings=66, min_az=14, f=95e9, mode=1, model=0, scaling="weak"),
     "small": dict(name="config2_1k_ray_beam", n_rays=1025, N_rings=7, min_az=20, f=95e9, mode=1, model=0, scaling="weak"),
@@ -392,7 +396,7 @@ def run_gpu_arm(args, wl):
     if wl == "config5":
         for te0, pos, dirs, w, f, bid, nb in config5_groups(args.c5_angles):
             pl = tj.Plasma(*hot_arrays(te0).values(), build="device")
-            idx = shard_indices(len(w), rank, world, "block_cyclic", 1025)
+            idx = shard_indices(len(w), rank, world, "block_cyclic", C5_BLOCK)
             plasmas.append(pl)
             bundles.append(DeviceBundle(L, _lib, ctx, pl.handle(ctx), pos[idx], dirs[idx], w[idx], f[idx], 1, opt, bid[idx], nb))
     else:
@@ -484,7 +488,7 @@ def run_gpu_arm(args, wl):
             for (te0, p5, d5, w5, f5, b5, nb), plq in zip(groups5, plasmas):
                 tj.trace_bundle(plq, p5, d5, w5, f5, 1, S_MAX, np.linspace(0.0, 1.0, N_PSI), ctx=ctx, options=opt, beam_id=b5, n_beams=nb)
         groups5 = [(te0, p5[i5], d5[i5], w5[i5], f5[i5], b5[i5], nb) for (te0, p5, d5, w5, f5, b5, nb) in config5_groups(args.c5_angles)
-                   for i5 in [shard_indices(len(w5), rank, world, "block_cyclic", 1025)]]
+                   for i5 in [shard_indices(len(w5), rank, world, "block_cyclic", C5_BLOCK)]]
         barrier()
         t0 = time.perf_counter()
         e2e_step()
@@ -526,7 +530,9 @@ def run_gpu_arm(args, wl):
         line = {"metric": "ray-steps/s", "value": steps_all / (ms_per_step * 1e-3), "unit": "ray-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": W["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "sharding": {"n_rays_this_gpu": n, "kind": "one beam per rank" if W["scaling"] == "weak" else "beams dealt round-robin (block-cyclic, 1025 rays)",
+                "sharding": {"n_rays_this_gpu": n, "kind": "one beam per rank" if W["scaling"] == "weak" else
+                             (f"{C5_BLOCK}-ray blocks dealt round-robin: every rank traces 1/N of every beam" if wl == "config5" else
+                              "beams dealt round-robin (block-cyclic, 1025 rays)"),
                              "schedule": args.schedule, "lanes_per_ray": args.lanes_per_ray},
                 "rays_per_s": rays_all / (ms_per_step * 1e-3), "rays_total": int(rays_all), "rays_ok": int(rays_ok.item()),
                 "e2e": {"value": steps_all / (e2e_ms * 1e-3), "unit": "ray-steps/s", "h2d_bytes_per_step": e2e["h2d"],
