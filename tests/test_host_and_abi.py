@@ -160,3 +160,21 @@ def test_product_never_touches_the_oracle():
     assert "oracle" not in out
     code = "import sys; sys.path.insert(0, %r); import torj_jl_b200; print(any('oracle' in m for m in sys.modules))" % ROOT
     assert subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout.strip() == "False"
+
+
+def test_config5_scan_sharding_gives_every_rank_a_share_of_every_beam():
+    """bench.py deals the rays of a multi-beam scan to the ranks in C5_BLOCK-ray blocks: a partition of the bundle, the same
+    number of rays per rank to within one block, and every rank holds rays of every 1 025-ray beam (whole beams per rank left
+    ranks with cheap beams idle: profiles/README.md, config 5)."""
+    import bench
+    from torj_jl_b200.distributed import shard_indices
+
+    n, world = 16 * 1025, 8
+    beam = np.arange(n) // 1025
+    parts = [shard_indices(n, r, world, "block_cyclic", bench.C5_BLOCK) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= bench.C5_BLOCK
+    for p in parts:
+        per_beam = np.bincount(beam[p], minlength=16)
+        assert per_beam.min() >= 1025 // world - bench.C5_BLOCK and per_beam.max() <= 1025 // world + 2 * bench.C5_BLOCK
